@@ -1,0 +1,720 @@
+// Host side of the decoder and the C ABI (include/qldpc_b200.h).  Everything that decodes runs on the GPU;
+// without a usable device the calls fail with QLDPC_ERR_NO_DEVICE -- there is no CPU path in this library.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <cstdio>
+#include <cstring>
+#include <random>
+#include <string>
+#include <vector>
+
+#include "../../include/qldpc_b200.h"
+#include "code.h"
+#include "kernels.cuh"
+
+using namespace qldpc;
+
+struct qldpc_code {
+  Code* c;
+};
+
+namespace {
+
+thread_local std::string g_err;
+int fail(int code, const std::string& msg) {
+  g_err = msg;
+  return code;
+}
+
+#define CU_TRY(expr)                                                                                  \
+  do {                                                                                                \
+    cudaError_t e_ = (expr);                                                                          \
+    if (e_ != cudaSuccess) {                                                                          \
+      cudaGetLastError();                                                                             \
+      return fail(e_ == cudaErrorNoDevice || e_ == cudaErrorInsufficientDriver ? QLDPC_ERR_NO_DEVICE  \
+                                                                               : QLDPC_ERR_CUDA,      \
+                  std::string(#expr) + ": " + cudaGetErrorString(e_));                                \
+    }                                                                                                 \
+  } while (0)
+
+struct DevSide {
+  int m = 0, dc = 0, dv = 0, E = 0, mw = 0;
+  uint16_t* vrow = nullptr;  // [dv][n]
+  uint16_t* cvar = nullptr;  // [dc][m]
+  BpLaunch cfg, user;        // resolved configuration / user overrides
+  bool cfg_ok = false;
+  std::string cfg_err;
+};
+
+template <typename T>
+cudaError_t dev_alloc(T*& p, size_t count) {
+  return cudaMalloc((void**)&p, std::max<size_t>(count, 1) * sizeof(T));
+}
+
+}  // namespace
+
+struct qldpc_decoder {
+  Code code;
+  int device = 0, num_sms = 0, chunk = 0;
+  int n = 0, nw = 0;
+  cudaStream_t own_stream = nullptr, stream = nullptr;
+  DevSide s[2];
+  uint32_t *errX = nullptr, *errZ = nullptr, *synX = nullptr, *synZ = nullptr, *decX = nullptr, *decZ = nullptr;
+  uint8_t *sfX = nullptr, *sfZ = nullptr, *fflags = nullptr;
+  uint32_t *itX = nullptr, *itZ = nullptr;
+  unsigned long long* counters = nullptr;
+  unsigned int* queues = nullptr;  // [2]
+  uint32_t *lx = nullptr, *lz = nullptr, *lm = nullptr;
+  int lx_rows = 0, lz_rows = 0, lm_rows = 0;
+  void* stage = nullptr;  // device staging for one-element-per-bit I/O
+  size_t stage_bytes = 0;
+  uint32_t* pin = nullptr;  // pinned host staging for the weight-W generator
+  size_t pin_words = 0;
+
+  ~qldpc_decoder() {
+    cudaSetDevice(device);
+    for (int i = 0; i < 2; ++i) { cudaFree(s[i].vrow); cudaFree(s[i].cvar); }
+    cudaFree(errX); cudaFree(errZ); cudaFree(synX); cudaFree(synZ); cudaFree(decX); cudaFree(decZ);
+    cudaFree(sfX); cudaFree(sfZ); cudaFree(fflags); cudaFree(itX); cudaFree(itZ);
+    cudaFree(counters); cudaFree(queues); cudaFree(lx); cudaFree(lz); cudaFree(lm); cudaFree(stage);
+    if (pin) cudaFreeHost(pin);
+    if (own_stream) cudaStreamDestroy(own_stream);
+  }
+};
+
+namespace {
+
+int ensure_stage(qldpc_decoder* d, size_t bytes) {
+  if (bytes <= d->stage_bytes) return QLDPC_OK;
+  cudaFree(d->stage);
+  d->stage = nullptr;
+  d->stage_bytes = 0;
+  CU_TRY(cudaMalloc(&d->stage, bytes));
+  d->stage_bytes = bytes;
+  return QLDPC_OK;
+}
+
+// logical rows [r0, r0+rows) restricted to bit-columns [c0, c0 + 32*words) -> transposed, row-padded LT[w][rows_pad]
+int upload_logical(const BitMatrix& L, int r0, int rows, int c0_word_of, int words, int n, bool z_part, uint32_t*& dst) {
+  (void)c0_word_of;
+  dst = nullptr;
+  if (rows == 0) return QLDPC_OK;
+  const int rows_pad = (rows + 31) & ~31;
+  std::vector<uint32_t> t((size_t)words * rows_pad, 0u);
+  const int nw = (n + 31) / 32;
+  for (int r = 0; r < rows; ++r)
+    for (int col = 0; col < 2 * n; ++col)
+      if (L.get(r0 + r, col)) {
+        int w, b;
+        if (col < n) {
+          if (z_part) continue;
+          w = col >> 5; b = col & 31;
+        } else {
+          const int zc = col - n;
+          w = (z_part ? 0 : nw) + (zc >> 5); b = zc & 31;
+        }
+        if (w < words) t[(size_t)w * rows_pad + r] |= 1u << b;
+      }
+  CU_TRY(dev_alloc(dst, t.size()));
+  CU_TRY(cudaMemcpy(dst, t.data(), t.size() * sizeof(uint32_t), cudaMemcpyHostToDevice));
+  return QLDPC_OK;
+}
+
+int resolve_config(qldpc_decoder* d, int side) {
+  DevSide& s = d->s[side];
+  BpLaunch cfg = s.user;
+  const char* why = "";
+  s.cfg_ok = bp_configure(s.dc, s.dv, s.m, d->n, d->num_sms, cfg, &why);
+  if (!s.cfg_ok) {
+    s.cfg_err = why;
+    return fail(QLDPC_ERR_UNSUPPORTED, s.cfg_err);
+  }
+  s.cfg = cfg;
+  return QLDPC_OK;
+}
+
+// BP on both sides over nf frames whose bit-packed syndromes are resident on the device.
+int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf, float errorProbability, int maxIterations,
+           uint32_t* decX, uint32_t* decZ, uint8_t* sfX, uint8_t* sfZ, uint32_t* itX, uint32_t* itZ, int only_side = -1,
+           float* trace_q = nullptr, float* trace_r = nullptr, int trace_cap = 0) {
+  if (nf <= 0) return QLDPC_OK;
+  const float prior = 2.0f / 3.0f * errorProbability;  // DecoderCPU.h:259, same float expression
+  CU_TRY(cudaMemsetAsync(d->queues, 0, 2 * sizeof(unsigned int), d->stream));
+  for (int side = 0; side < 2; ++side) {
+    if (only_side >= 0 && side != only_side) continue;
+    DevSide& s = d->s[side];
+    if (!s.cfg_ok) return fail(QLDPC_ERR_UNSUPPORTED, s.cfg_err);
+    BpArgs a;
+    a.syn = side ? synZ : synX;
+    a.dec = side ? decZ : decX;
+    a.flags = side ? sfZ : sfX;
+    a.iters = side ? itZ : itX;
+    a.vrow = s.vrow;
+    a.cvar = s.cvar;
+    a.queue = d->queues + side;
+    a.m = s.m; a.n = d->n; a.mw = s.mw; a.nw = d->nw;
+    a.nframes = nf;
+    a.maxit = maxIterations;
+    a.prior = prior;
+    a.trace_q = trace_q; a.trace_r = trace_r; a.trace_cap = trace_cap;
+    CU_TRY(bp_launch(s.dc, s.dv, s.cfg, a, nf, d->stream));
+  }
+  return QLDPC_OK;
+}
+
+int run_stats(qldpc_decoder* d, int nf, uint8_t* fflags) {
+  StatsArgs a;
+  a.errX = d->errX; a.errZ = d->errZ; a.decX = d->decX; a.decZ = d->decZ;
+  a.sfX = d->sfX; a.sfZ = d->sfZ; a.itX = d->itX; a.itZ = d->itZ;
+  a.lx = d->lx; a.lz = d->lz; a.lm = d->lm;
+  a.lx_rows = d->lx_rows; a.lz_rows = d->lz_rows; a.lm_rows = d->lm_rows;
+  a.nframes = nf; a.nw = d->nw;
+  a.counters = d->counters;
+  a.fflags = fflags;
+  CU_TRY(launch_stats(a, d->stream));
+  return QLDPC_OK;
+}
+
+int run_syndrome(qldpc_decoder* d, int nf) {
+  CU_TRY(launch_syndrome(d->errX, d->errZ, nf, d->n, d->nw, d->s[0].cvar, d->s[0].m, d->s[0].dc, d->s[0].mw, d->synX,
+                         d->s[1].cvar, d->s[1].m, d->s[1].dc, d->s[1].mw, d->synZ, d->stream));
+  return QLDPC_OK;
+}
+
+int check_common(qldpc_decoder* d, int64_t nframes, int maxIterations) {
+  if (!d) return fail(QLDPC_ERR_ARG, "null decoder");
+  if (nframes < 0) return fail(QLDPC_ERR_ARG, "negative frame count");
+  if (maxIterations < 1) return fail(QLDPC_ERR_ARG, "maxIterations must be >= 1");
+  CU_TRY(cudaSetDevice(d->device));
+  return QLDPC_OK;
+}
+
+// After errors + syndromes of one chunk are resident: decode, reduce, copy the optional per-frame outputs.
+int finish_chunk(qldpc_decoder* d, int nf, int64_t off, float ep, int maxit, uint8_t* perFrameFlags, uint32_t* perFrameIters) {
+  int rc = run_bp(d, d->synX, d->synZ, nf, ep, maxit, d->decX, d->decZ, d->sfX, d->sfZ, d->itX, d->itZ);
+  if (rc) return rc;
+  rc = run_stats(d, nf, d->fflags);
+  if (rc) return rc;
+  if (perFrameFlags) CU_TRY(cudaMemcpyAsync(perFrameFlags + off, d->fflags, (size_t)nf, cudaMemcpyDeviceToHost, d->stream));
+  if (perFrameIters) {
+    std::vector<uint32_t> hx(nf), hz(nf);
+    CU_TRY(cudaMemcpyAsync(hx.data(), d->itX, (size_t)nf * 4, cudaMemcpyDeviceToHost, d->stream));
+    CU_TRY(cudaMemcpyAsync(hz.data(), d->itZ, (size_t)nf * 4, cudaMemcpyDeviceToHost, d->stream));
+    CU_TRY(cudaStreamSynchronize(d->stream));
+    for (int f = 0; f < nf; ++f) {
+      perFrameIters[2 * (off + f)] = hx[f];
+      perFrameIters[2 * (off + f) + 1] = hz[f];
+    }
+  }
+  return QLDPC_OK;
+}
+
+int read_counters(qldpc_decoder* d, uint64_t* counters) {
+  unsigned long long h[QLDPC_NUM_COUNTERS];
+  CU_TRY(cudaMemcpyAsync(h, d->counters, sizeof h, cudaMemcpyDeviceToHost, d->stream));
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  if (counters)
+    for (int i = 0; i < QLDPC_NUM_COUNTERS; ++i) counters[i] = (uint64_t)h[i];
+  return QLDPC_OK;
+}
+
+template <typename F>
+int guarded(F&& f) {
+  try {
+    return f();
+  } catch (const std::string& s) {
+    return fail(QLDPC_ERR_ARG, s);
+  } catch (const std::bad_alloc&) {
+    return fail(QLDPC_ERR_ARG, "out of host memory");
+  } catch (const std::exception& e) {
+    return fail(QLDPC_ERR_ARG, e.what());
+  }
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* qldpc_version(void) { return "qldpc_b200 0.1 (sm_100a)"; }
+const char* qldpc_last_error(void) { return g_err.c_str(); }
+
+// ---------------------------------------------------------------------------------------------------- code
+
+int qldpc_code_create_qc(int J, int K, int L, int P, int sigma, int tau, qldpc_code** out) {
+  if (!out) return fail(QLDPC_ERR_ARG, "null out pointer");
+  return guarded([&] {
+    *out = new qldpc_code{code_from_qc(J, K, L, P, sigma, tau)};
+    return QLDPC_OK;
+  });
+}
+
+int qldpc_code_create_dense(int J, int K, int L, int P, int sigma, int tau, const int32_t* pcmX, const int32_t* pcmZ,
+                            const int32_t* iMinusP, qldpc_code** out) {
+  if (!out) return fail(QLDPC_ERR_ARG, "null out pointer");
+  return guarded([&] {
+    *out = new qldpc_code{code_from_dense(J, K, L, P, sigma, tau, pcmX, pcmZ, iMinusP)};
+    return QLDPC_OK;
+  });
+}
+
+int qldpc_code_create_from_file(const char* path, qldpc_code** out) {
+  if (!out || !path) return fail(QLDPC_ERR_ARG, "null argument");
+  try {
+    *out = new qldpc_code{code_from_file(path)};
+    return QLDPC_OK;
+  } catch (const std::string& s) {
+    return fail(s.rfind("Unable to", 0) == 0 ? QLDPC_ERR_IO : QLDPC_ERR_ARG, s);
+  } catch (const std::exception& e) {
+    return fail(QLDPC_ERR_ARG, e.what());
+  }
+}
+
+int qldpc_code_write_file(const qldpc_code* code, const char* path) {
+  if (!code || !path) return fail(QLDPC_ERR_ARG, "null argument");
+  try {
+    code_write_file(*code->c, path);
+    return QLDPC_OK;
+  } catch (const std::string& s) {
+    return fail(QLDPC_ERR_IO, s);
+  }
+}
+
+void qldpc_code_destroy(qldpc_code* code) {
+  if (code) {
+    delete code->c;
+    delete code;
+  }
+}
+
+int qldpc_code_get_info(const qldpc_code* code, qldpc_code_info* o) {
+  if (!code || !o) return fail(QLDPC_ERR_ARG, "null argument");
+  const Code& c = *code->c;
+  o->J = c.J; o->K = c.K; o->L = c.L; o->P = c.P; o->sigma = c.sigma; o->tau = c.tau;
+  o->n = c.n; o->mX = c.side[0].m; o->mZ = c.side[1].m;
+  o->dcX = c.side[0].dc; o->dcZ = c.side[1].dc; o->dvX = c.side[0].dv; o->dvZ = c.side[1].dv;
+  o->EX = c.side[0].E; o->EZ = c.side[1].E;
+  o->logical_rows = c.logical.rows;
+  o->is_qc = c.is_qc;
+  o->logical_from_file = c.logical_from_file;
+  return QLDPC_OK;
+}
+
+int qldpc_code_name(const qldpc_code* code, char* out, int cap) {
+  if (!code || !out || cap < 1) return fail(QLDPC_ERR_ARG, "null argument");
+  const std::string s = code->c->name();
+  snprintf(out, (size_t)cap, "%s", s.c_str());
+  return QLDPC_OK;
+}
+
+int qldpc_code_exponents(const qldpc_code* code, int side, int32_t* out) {
+  if (!code || !out || side < 0 || side > 1) return fail(QLDPC_ERR_ARG, "bad argument");
+  const auto& h = code->c->side[side].hexp;
+  if (h.empty()) return fail(QLDPC_ERR_ARG, "code is not quasi-cyclic in its (J,K,L,P,sigma,tau)");
+  std::copy(h.begin(), h.end(), out);
+  return QLDPC_OK;
+}
+
+int qldpc_code_csr(const qldpc_code* code, int side, int32_t* chk_var) {
+  if (!code || !chk_var || side < 0 || side > 1) return fail(QLDPC_ERR_ARG, "bad argument");
+  const auto& t = code->c->side[side];
+  std::copy(t.chk_var.begin(), t.chk_var.end(), chk_var);
+  return QLDPC_OK;
+}
+
+int qldpc_code_csc(const qldpc_code* code, int side, int32_t* var_chk, int32_t* var_edge) {
+  if (!code || !var_chk || side < 0 || side > 1) return fail(QLDPC_ERR_ARG, "bad argument");
+  const auto& t = code->c->side[side];
+  std::copy(t.var_chk.begin(), t.var_chk.end(), var_chk);
+  if (var_edge) std::copy(t.var_edge.begin(), t.var_edge.end(), var_edge);
+  return QLDPC_OK;
+}
+
+int qldpc_code_dense(const qldpc_code* code, int which, int32_t* out) {
+  if (!code || !out || which < 0 || which > 2) return fail(QLDPC_ERR_ARG, "bad argument");
+  const Code& c = *code->c;
+  if (which < 2) {
+    c.dense_pcm(which, out);
+  } else {
+    for (int r = 0; r < c.logical.rows; ++r)
+      for (int col = 0; col < 2 * c.n; ++col) out[(size_t)r * 2 * c.n + col] = c.logical.get(r, col);
+  }
+  return QLDPC_OK;
+}
+
+int qldpc_code_is_css(const qldpc_code* code) {
+  if (!code) return fail(QLDPC_ERR_ARG, "null argument");
+  return code->c->is_css() ? 1 : 0;
+}
+
+int qldpc_code_syndrome(const qldpc_code* code, int side, const int32_t* errors, int32_t* syndrome) {
+  if (!code || !errors || !syndrome || side < 0 || side > 1) return fail(QLDPC_ERR_ARG, "bad argument");
+  code->c->syndrome(side, errors, syndrome);
+  return QLDPC_OK;
+}
+
+int qldpc_code_check_logical(const qldpc_code* code, const int32_t* errors2n) {
+  if (!code || !errors2n) return fail(QLDPC_ERR_ARG, "null argument");
+  return code->c->check_logical(errors2n) ? 1 : 0;
+}
+
+// ------------------------------------------------------------------------------------------------- decoder
+
+int qldpc_decoder_create(const qldpc_code* code, int device_ordinal, int max_frames, qldpc_decoder** out) {
+  if (!code || !out) return fail(QLDPC_ERR_ARG, "null argument");
+  int ndev = 0;
+  cudaError_t e = cudaGetDeviceCount(&ndev);
+  if (e != cudaSuccess || ndev == 0) {
+    cudaGetLastError();
+    return fail(QLDPC_ERR_NO_DEVICE,
+                std::string("no usable CUDA device (") + cudaGetErrorString(e) + "); this library has no CPU decode path");
+  }
+  if (device_ordinal < 0) CU_TRY(cudaGetDevice(&device_ordinal));
+  if (device_ordinal >= ndev) return fail(QLDPC_ERR_ARG, "device ordinal out of range");
+  CU_TRY(cudaSetDevice(device_ordinal));
+  cudaDeviceProp prop;
+  CU_TRY(cudaGetDeviceProperties(&prop, device_ordinal));
+  if (prop.major < 10)
+    return fail(QLDPC_ERR_NO_DEVICE, std::string("device ") + prop.name + " is not sm_100 class; kernels are built for sm_100a only");
+
+  qldpc_decoder* d = new qldpc_decoder;
+  d->code = *code->c;
+  d->device = device_ordinal;
+  d->num_sms = prop.multiProcessorCount;
+  d->chunk = max_frames > 0 ? max_frames : (1 << 18);
+  d->n = d->code.n;
+  d->nw = (d->n + 31) / 32;
+  auto bail = [&](int rc) {
+    delete d;
+    return rc;
+  };
+#define D_TRY(expr)                          \
+  do {                                       \
+    int rc_ = [&]() -> int {                 \
+      CU_TRY(expr);                          \
+      return QLDPC_OK;                       \
+    }();                                     \
+    if (rc_) return bail(rc_);               \
+  } while (0)
+  D_TRY(cudaStreamCreateWithFlags(&d->own_stream, cudaStreamNonBlocking));
+  d->stream = d->own_stream;
+  const int n = d->n;
+  for (int side = 0; side < 2; ++side) {
+    const SideTables& t = d->code.side[side];
+    DevSide& s = d->s[side];
+    s.m = t.m; s.dc = t.dc; s.dv = t.dv; s.E = t.E; s.mw = (t.m + 31) / 32;
+    if (t.E >= 65536) {
+      s.cfg_ok = false;
+      s.cfg_err = "code too large for the shared-memory-resident BP kernel";
+      continue;
+    }
+    std::vector<uint16_t> vrow((size_t)t.E), cvar((size_t)t.E);
+    for (int v = 0; v < n; ++v)
+      for (int k = 0; k < t.dv; ++k) {
+        const int edge = t.var_edge[(size_t)v * t.dv + k];
+        const int e = edge / t.dc, i = edge % t.dc;
+        vrow[(size_t)k * n + v] = (uint16_t)(i * t.m + e);
+      }
+    for (int e = 0; e < t.m; ++e)
+      for (int i = 0; i < t.dc; ++i) cvar[(size_t)i * t.m + e] = (uint16_t)t.chk_var[(size_t)e * t.dc + i];
+    D_TRY(dev_alloc(s.vrow, vrow.size()));
+    D_TRY(dev_alloc(s.cvar, cvar.size()));
+    D_TRY(cudaMemcpy(s.vrow, vrow.data(), vrow.size() * 2, cudaMemcpyHostToDevice));
+    D_TRY(cudaMemcpy(s.cvar, cvar.data(), cvar.size() * 2, cudaMemcpyHostToDevice));
+    resolve_config(d, side);  // failure is reported when the side is first used
+  }
+  const size_t F = (size_t)d->chunk;
+  D_TRY(dev_alloc(d->errX, F * d->nw));
+  D_TRY(dev_alloc(d->errZ, F * d->nw));
+  D_TRY(dev_alloc(d->decX, F * d->nw));
+  D_TRY(dev_alloc(d->decZ, F * d->nw));
+  D_TRY(dev_alloc(d->synX, F * d->s[0].mw));
+  D_TRY(dev_alloc(d->synZ, F * d->s[1].mw));
+  D_TRY(dev_alloc(d->sfX, F));
+  D_TRY(dev_alloc(d->sfZ, F));
+  D_TRY(dev_alloc(d->fflags, F));
+  D_TRY(dev_alloc(d->itX, F));
+  D_TRY(dev_alloc(d->itZ, F));
+  D_TRY(dev_alloc(d->counters, (size_t)QLDPC_NUM_COUNTERS));
+  D_TRY(dev_alloc(d->queues, (size_t)2));
+  const Code& c = d->code;
+  d->lx_rows = c.lx; d->lz_rows = c.lz; d->lm_rows = c.lm;
+  int rc = upload_logical(c.logical, 0, c.lx, 0, d->nw, n, false, d->lx);
+  if (!rc) rc = upload_logical(c.logical, c.lx, c.lz, 0, d->nw, n, true, d->lz);
+  if (!rc) rc = upload_logical(c.logical, c.lx + c.lz, c.lm, 0, 2 * d->nw, n, false, d->lm);
+  if (rc) return bail(rc);
+#undef D_TRY
+  *out = d;
+  return QLDPC_OK;
+}
+
+void qldpc_decoder_destroy(qldpc_decoder* dec) { delete dec; }
+
+int qldpc_decoder_set_stream(qldpc_decoder* dec, void* cuda_stream) {
+  if (!dec) return fail(QLDPC_ERR_ARG, "null decoder");
+  dec->stream = cuda_stream ? (cudaStream_t)cuda_stream : dec->own_stream;
+  return QLDPC_OK;
+}
+
+int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, int threads_per_cta, int ctas_per_sm) {
+  if (!dec || side < 0 || side > 1) return fail(QLDPC_ERR_ARG, "bad argument");
+  CU_TRY(cudaSetDevice(dec->device));
+  BpLaunch keep = dec->s[side].user;
+  dec->s[side].user = BpLaunch();
+  dec->s[side].user.vec = frames_per_tile;
+  dec->s[side].user.threads = threads_per_cta;
+  dec->s[side].user.ctas_per_sm = ctas_per_sm;
+  int rc = resolve_config(dec, side);
+  if (rc) {
+    dec->s[side].user = keep;
+    resolve_config(dec, side);
+    return fail(rc, "configuration rejected");
+  }
+  return QLDPC_OK;
+}
+
+int qldpc_decoder_launch_info(qldpc_decoder* dec, int side, int32_t out[8]) {
+  if (!dec || !out || side < 0 || side > 1) return fail(QLDPC_ERR_ARG, "bad argument");
+  const DevSide& s = dec->s[side];
+  if (!s.cfg_ok) return fail(QLDPC_ERR_UNSUPPORTED, s.cfg_err);
+  int v[8] = {s.cfg.vec, s.cfg.threads, s.cfg.ctas_per_sm, s.cfg.grid, s.cfg.smem, s.cfg.regs, dec->num_sms, dec->chunk};
+  std::copy(v, v + 8, out);
+  return QLDPC_OK;
+}
+
+int qldpc_decode_batch_device(qldpc_decoder* dec, const uint32_t* d_synX, const uint32_t* d_synZ, int64_t nframes,
+                              float errorProbability, int maxIterations, uint32_t* d_outX, uint32_t* d_outZ,
+                              uint8_t* d_outFlags, uint32_t* d_outIters) {
+  int rc = check_common(dec, nframes, maxIterations);
+  if (rc) return rc;
+  if (!d_synX || !d_synZ || !d_outX || !d_outZ || !d_outFlags) return fail(QLDPC_ERR_ARG, "null buffer");
+  qldpc_decoder* d = dec;
+  for (int64_t off = 0; off < nframes; off += d->chunk) {
+    const int nf = (int)std::min<int64_t>(d->chunk, nframes - off);
+    rc = run_bp(d, d_synX + off * d->s[0].mw, d_synZ + off * d->s[1].mw, nf, errorProbability, maxIterations,
+                d_outX + off * d->nw, d_outZ + off * d->nw, d->sfX, d->sfZ, d->itX, d->itZ);
+    if (rc) return rc;
+    CU_TRY(launch_merge_flags(d->sfX, d->sfZ, nf, d_outFlags + off, d->stream));
+    if (d_outIters) {
+      CU_TRY(cudaMemcpy2DAsync(d_outIters + 2 * off, 8, d->itX, 4, 4, (size_t)nf, cudaMemcpyDeviceToDevice, d->stream));
+      CU_TRY(cudaMemcpy2DAsync(d_outIters + 2 * off + 1, 8, d->itZ, 4, 4, (size_t)nf, cudaMemcpyDeviceToDevice, d->stream));
+    }
+  }
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  return QLDPC_OK;
+}
+
+int qldpc_decode_batch(qldpc_decoder* dec, const uint8_t* synX, const uint8_t* synZ, int64_t nframes,
+                       float errorProbability, int maxIterations, uint8_t* outX, uint8_t* outZ, uint8_t* outFlags,
+                       uint32_t* outIters) {
+  int rc = check_common(dec, nframes, maxIterations);
+  if (rc) return rc;
+  if (!synX || !synZ || !outX || !outZ || !outFlags) return fail(QLDPC_ERR_ARG, "null buffer");
+  qldpc_decoder* d = dec;
+  const int n = d->n, mX = d->s[0].m, mZ = d->s[1].m;
+  const size_t per = (size_t)std::max(n, std::max(mX, mZ));
+  rc = ensure_stage(d, 2 * per * std::min<int64_t>(d->chunk, std::max<int64_t>(nframes, 1)));
+  if (rc) return rc;
+  for (int64_t off = 0; off < nframes; off += d->chunk) {
+    const int nf = (int)std::min<int64_t>(d->chunk, nframes - off);
+    uint8_t* st0 = (uint8_t*)d->stage;
+    uint8_t* st1 = st0 + per * nf;
+    CU_TRY(cudaMemcpyAsync(st0, synX + off * mX, (size_t)nf * mX, cudaMemcpyHostToDevice, d->stream));
+    CU_TRY(cudaMemcpyAsync(st1, synZ + off * mZ, (size_t)nf * mZ, cudaMemcpyHostToDevice, d->stream));
+    CU_TRY(launch_pack(st0, 1, nf, mX, d->s[0].mw, d->synX, d->stream));
+    CU_TRY(launch_pack(st1, 1, nf, mZ, d->s[1].mw, d->synZ, d->stream));
+    rc = run_bp(d, d->synX, d->synZ, nf, errorProbability, maxIterations, d->decX, d->decZ, d->sfX, d->sfZ, d->itX, d->itZ);
+    if (rc) return rc;
+    CU_TRY(launch_unpack(d->decX, nf, n, d->nw, st0, d->stream));
+    CU_TRY(launch_unpack(d->decZ, nf, n, d->nw, st1, d->stream));
+    CU_TRY(launch_merge_flags(d->sfX, d->sfZ, nf, d->fflags, d->stream));
+    CU_TRY(cudaMemcpyAsync(outX + off * n, st0, (size_t)nf * n, cudaMemcpyDeviceToHost, d->stream));
+    CU_TRY(cudaMemcpyAsync(outZ + off * n, st1, (size_t)nf * n, cudaMemcpyDeviceToHost, d->stream));
+    CU_TRY(cudaMemcpyAsync(outFlags + off, d->fflags, (size_t)nf, cudaMemcpyDeviceToHost, d->stream));
+    if (outIters) {
+      CU_TRY(cudaMemcpy2DAsync(outIters + 2 * off, 8, d->itX, 4, 4, (size_t)nf, cudaMemcpyDeviceToHost, d->stream));
+      CU_TRY(cudaMemcpy2DAsync(outIters + 2 * off + 1, 8, d->itZ, 4, 4, (size_t)nf, cudaMemcpyDeviceToHost, d->stream));
+    }
+    CU_TRY(cudaStreamSynchronize(d->stream));
+  }
+  return QLDPC_OK;
+}
+
+int qldpc_get_statistics_depolarizing(qldpc_decoder* dec, uint64_t seed, uint64_t first_frame, int64_t nframes,
+                                      float p, int maxIterations, uint64_t* counters, uint8_t* perFrameFlags,
+                                      uint32_t* perFrameIters) {
+  int rc = check_common(dec, nframes, maxIterations);
+  if (rc) return rc;
+  qldpc_decoder* d = dec;
+  const Thresholds thr = depolarizing_thresholds(p);
+  CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
+  for (int64_t off = 0; off < nframes; off += d->chunk) {
+    const int nf = (int)std::min<int64_t>(d->chunk, nframes - off);
+    CU_TRY(launch_generate(seed, first_frame + (uint64_t)off, nf, d->n, d->nw, thr, d->errX, d->errZ, d->stream));
+    rc = run_syndrome(d, nf);
+    if (rc) return rc;
+    rc = finish_chunk(d, nf, off, p, maxIterations, perFrameFlags, perFrameIters);
+    if (rc) return rc;
+  }
+  return read_counters(d, counters);
+}
+
+// MSVC's uniform_int_distribution<int>(0, R-1) over std::mt19937: the mapping the published
+// results files were generated with; std::mt19937 itself is specified by the C++ standard.
+static inline uint32_t msvc_uniform(std::mt19937& g, uint32_t R) {
+  for (;;) {
+    const uint32_t u = (uint32_t)g();
+    if (u / R < 0xFFFFFFFFu / R || 0xFFFFFFFFu % R == R - 1) return u % R;
+  }
+}
+
+int qldpc_get_statistics_weightw(qldpc_decoder* dec, int errorWeight, int64_t numErrors, float errorProbability,
+                                 int maxIterations, uint32_t seed, uint64_t* counters, uint8_t* perFrameFlags,
+                                 uint32_t* perFrameIters) {
+  int rc = check_common(dec, numErrors, maxIterations);
+  if (rc) return rc;
+  if (errorWeight < 0) return fail(QLDPC_ERR_ARG, "negative error weight");
+  qldpc_decoder* d = dec;
+  const int n = d->n, nw = d->nw;
+  const size_t need = (size_t)2 * nw * std::min<int64_t>(d->chunk, std::max<int64_t>(numErrors, 1));
+  if (need > d->pin_words) {
+    if (d->pin) cudaFreeHost(d->pin);
+    d->pin = nullptr;
+    d->pin_words = 0;
+    CU_TRY(cudaMallocHost((void**)&d->pin, need * sizeof(uint32_t)));
+    d->pin_words = need;
+  }
+  std::mt19937 mt(seed);  // DecoderCPU.h:394
+  CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
+  for (int64_t off = 0; off < numErrors; off += d->chunk) {
+    const int nf = (int)std::min<int64_t>(d->chunk, numErrors - off);
+    uint32_t* hx = d->pin;
+    uint32_t* hz = d->pin + (size_t)nf * nw;
+    std::memset(d->pin, 0, (size_t)2 * nf * nw * sizeof(uint32_t));
+    for (int f = 0; f < nf; ++f)
+      for (int i = 0; i < errorWeight; ++i) {  // DecoderCPU.h:449-458: index, then type; collisions allowed
+        const uint32_t index = msvc_uniform(mt, (uint32_t)n);
+        const uint32_t error = msvc_uniform(mt, 3u);
+        if (error == 0 || error == 1) hx[(size_t)f * nw + (index >> 5)] |= 1u << (index & 31);
+        if (error == 2 || error == 1) hz[(size_t)f * nw + (index >> 5)] |= 1u << (index & 31);
+      }
+    CU_TRY(cudaMemcpyAsync(d->errX, hx, (size_t)nf * nw * 4, cudaMemcpyHostToDevice, d->stream));
+    CU_TRY(cudaMemcpyAsync(d->errZ, hz, (size_t)nf * nw * 4, cudaMemcpyHostToDevice, d->stream));
+    rc = run_syndrome(d, nf);
+    if (rc) return rc;
+    rc = finish_chunk(d, nf, off, errorProbability, maxIterations, perFrameFlags, perFrameIters);
+    if (rc) return rc;
+    CU_TRY(cudaStreamSynchronize(d->stream));  // the pinned buffer is rewritten for the next chunk
+  }
+  return read_counters(d, counters);
+}
+
+static int stats_from_errors(qldpc_decoder* d, const void* xErrors, const void* zErrors, int elem, int64_t numErrors,
+                             float errorProbability, int maxIterations, uint64_t* counters, uint8_t* perFrameFlags,
+                             uint32_t* perFrameIters) {
+  int rc = check_common(d, numErrors, maxIterations);
+  if (rc) return rc;
+  if (!xErrors || !zErrors) return fail(QLDPC_ERR_ARG, "null buffer");
+  const int n = d->n;
+  const size_t row = (size_t)n * elem;
+  rc = ensure_stage(d, 2 * row * std::min<int64_t>(d->chunk, std::max<int64_t>(numErrors, 1)));
+  if (rc) return rc;
+  CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
+  for (int64_t off = 0; off < numErrors; off += d->chunk) {
+    const int nf = (int)std::min<int64_t>(d->chunk, numErrors - off);
+    uint8_t* st0 = (uint8_t*)d->stage;
+    uint8_t* st1 = st0 + row * nf;
+    CU_TRY(cudaMemcpyAsync(st0, (const uint8_t*)xErrors + off * row, row * nf, cudaMemcpyHostToDevice, d->stream));
+    CU_TRY(cudaMemcpyAsync(st1, (const uint8_t*)zErrors + off * row, row * nf, cudaMemcpyHostToDevice, d->stream));
+    CU_TRY(launch_pack(st0, elem, nf, n, d->nw, d->errX, d->stream));
+    CU_TRY(launch_pack(st1, elem, nf, n, d->nw, d->errZ, d->stream));
+    rc = run_syndrome(d, nf);
+    if (rc) return rc;
+    rc = finish_chunk(d, nf, off, errorProbability, maxIterations, perFrameFlags, perFrameIters);
+    if (rc) return rc;
+  }
+  return read_counters(d, counters);
+}
+
+int qldpc_get_stats_from_errors_i32(qldpc_decoder* dec, const int32_t* xErrors, const int32_t* zErrors,
+                                    int64_t numErrors, float errorProbability, int maxIterations, uint64_t* counters,
+                                    uint8_t* perFrameFlags, uint32_t* perFrameIters) {
+  return stats_from_errors(dec, xErrors, zErrors, 4, numErrors, errorProbability, maxIterations, counters, perFrameFlags,
+                           perFrameIters);
+}
+
+int qldpc_get_stats_from_errors_u8(qldpc_decoder* dec, const uint8_t* xErrors, const uint8_t* zErrors,
+                                   int64_t numErrors, float errorProbability, int maxIterations, uint64_t* counters,
+                                   uint8_t* perFrameFlags, uint32_t* perFrameIters) {
+  return stats_from_errors(dec, xErrors, zErrors, 1, numErrors, errorProbability, maxIterations, counters, perFrameFlags,
+                           perFrameIters);
+}
+
+// -------------------------------------------------------------------------------------------------- taps
+
+int qldpc_debug_generate(qldpc_decoder* dec, uint64_t seed, uint64_t first_frame, int64_t nframes, float p,
+                         uint8_t* xerr, uint8_t* zerr, uint8_t* synX, uint8_t* synZ) {
+  int rc = check_common(dec, nframes, 1);
+  if (rc) return rc;
+  qldpc_decoder* d = dec;
+  const int n = d->n, mX = d->s[0].m, mZ = d->s[1].m;
+  const size_t per = (size_t)std::max(n, std::max(mX, mZ));
+  rc = ensure_stage(d, per * std::min<int64_t>(d->chunk, std::max<int64_t>(nframes, 1)));
+  if (rc) return rc;
+  const Thresholds thr = depolarizing_thresholds(p);
+  for (int64_t off = 0; off < nframes; off += d->chunk) {
+    const int nf = (int)std::min<int64_t>(d->chunk, nframes - off);
+    CU_TRY(launch_generate(seed, first_frame + (uint64_t)off, nf, n, d->nw, thr, d->errX, d->errZ, d->stream));
+    rc = run_syndrome(d, nf);
+    if (rc) return rc;
+    struct { const uint32_t* src; int cols, words; uint8_t* dst; } jobs[4] = {
+        {d->errX, n, d->nw, xerr}, {d->errZ, n, d->nw, zerr}, {d->synX, mX, d->s[0].mw, synX}, {d->synZ, mZ, d->s[1].mw, synZ}};
+    for (auto& j : jobs) {
+      if (!j.dst) continue;
+      CU_TRY(launch_unpack(j.src, nf, j.cols, j.words, (uint8_t*)d->stage, d->stream));
+      CU_TRY(cudaMemcpyAsync(j.dst + off * j.cols, d->stage, (size_t)nf * j.cols, cudaMemcpyDeviceToHost, d->stream));
+      CU_TRY(cudaStreamSynchronize(d->stream));
+    }
+  }
+  return QLDPC_OK;
+}
+
+int qldpc_debug_bp_trace(qldpc_decoder* dec, int side, const uint8_t* syn, int nframes, float errorProbability,
+                         int maxIterations, int cap_iters, float* q_trace, float* r_trace, uint32_t* iters) {
+  int rc = check_common(dec, nframes, maxIterations);
+  if (rc) return rc;
+  if (side < 0 || side > 1 || !syn || cap_iters < 1) return fail(QLDPC_ERR_ARG, "bad argument");
+  qldpc_decoder* d = dec;
+  if (nframes > d->chunk) return fail(QLDPC_ERR_ARG, "trace batch larger than max_frames");
+  const DevSide& s = d->s[side];
+  const size_t tsz = (size_t)nframes * cap_iters * s.E;
+  rc = ensure_stage(d, (size_t)nframes * s.m);
+  if (rc) return rc;
+  float *dq = nullptr, *dr = nullptr;
+  CU_TRY(dev_alloc(dq, tsz));
+  CU_TRY(dev_alloc(dr, tsz));
+  auto cleanup = [&](int r) {
+    cudaFree(dq);
+    cudaFree(dr);
+    return r;
+  };
+  uint32_t* dsyn = side ? d->synZ : d->synX;
+  rc = [&]() -> int {
+    CU_TRY(cudaMemsetAsync(dq, 0, tsz * 4, d->stream));
+    CU_TRY(cudaMemsetAsync(dr, 0, tsz * 4, d->stream));
+    CU_TRY(cudaMemcpyAsync(d->stage, syn, (size_t)nframes * s.m, cudaMemcpyHostToDevice, d->stream));
+    CU_TRY(launch_pack(d->stage, 1, nframes, s.m, s.mw, dsyn, d->stream));
+    int r = run_bp(d, d->synX, d->synZ, nframes, errorProbability, maxIterations, d->decX, d->decZ, d->sfX, d->sfZ, d->itX,
+                   d->itZ, side, dq, dr, cap_iters);
+    if (r) return r;
+    if (q_trace) CU_TRY(cudaMemcpyAsync(q_trace, dq, tsz * 4, cudaMemcpyDeviceToHost, d->stream));
+    if (r_trace) CU_TRY(cudaMemcpyAsync(r_trace, dr, tsz * 4, cudaMemcpyDeviceToHost, d->stream));
+    if (iters)
+      CU_TRY(cudaMemcpyAsync(iters, side ? d->itZ : d->itX, (size_t)nframes * 4, cudaMemcpyDeviceToHost, d->stream));
+    CU_TRY(cudaStreamSynchronize(d->stream));
+    return QLDPC_OK;
+  }();
+  return cleanup(rc);
+}
+
+}  // extern "C"

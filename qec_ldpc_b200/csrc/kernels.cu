@@ -1,0 +1,373 @@
+// Device code: BP tile-kernel instantiations and dispatch, Philox depolarizing-error generator, sparse
+// syndrome kernel, bit pack/unpack, and the on-device statistics reduction (CodeStatistics counters).
+#include "kernels.cuh"
+
+#include <algorithm>
+#include <cstdio>
+
+#include "../../include/qldpc_b200.h"
+
+namespace qldpc {
+
+// =====================================================================================================
+// BP dispatch
+// =====================================================================================================
+
+// Register budget: (MAXT, MINB) = (256, 2) lets the compiler use up to 128 registers; the tile kernels need
+// well under 100, which leaves 640+ resident threads per SM next to the shared-memory limit.
+constexpr int kMaxT = 256;
+constexpr int kMinB = 2;
+
+typedef void (*BpKernel)(const BpArgs);
+
+template <int DC, int DV>
+static BpKernel kernel_for_vec(int vec) {
+  switch (vec) {
+    case 4: return bp_tile_kernel<DC, DV, 4, kMaxT, kMinB>;
+    case 2: return bp_tile_kernel<DC, DV, 2, kMaxT, kMinB>;
+    case 1: return bp_tile_kernel<DC, DV, 1, kMaxT, kMinB>;
+  }
+  return nullptr;
+}
+
+static BpKernel lookup_kernel(int dc, int dv, int vec) {
+#define QLDPC_SHAPE(DC, DV) \
+  if (dc == DC && dv == DV) return kernel_for_vec<DC, DV>(vec);
+  QLDPC_SHAPE(6, 3)    // J3K3L6P7 (both sides)
+  QLDPC_SHAPE(10, 4)   // J4K5L10P61 X side
+  QLDPC_SHAPE(10, 5)   // J4K5L10P61 Z side
+  QLDPC_SHAPE(8, 4)    // J4K4L8P509 (both sides)
+  QLDPC_SHAPE(4, 2)
+  QLDPC_SHAPE(6, 2)
+  QLDPC_SHAPE(8, 3)
+  QLDPC_SHAPE(12, 5)
+  QLDPC_SHAPE(12, 6)
+#undef QLDPC_SHAPE
+  return nullptr;
+}
+
+bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, const char** why) {
+  static const char* kNoShape = "no compiled BP kernel for this (check degree, variable degree)";
+  static const char* kNoFit = "one frame of messages does not fit in shared memory (HBM-resident variant not built)";
+  static const char* kBadCfg = "invalid launch configuration";
+  if (!lookup_kernel(dc, dv, 1)) { *why = kNoShape; return false; }
+  const int E = m * dc, mw = (m + 31) / 32, nw = (n + 31) / 32;
+  if (E >= 65536) { *why = kNoFit; return false; }
+  int dev = 0, smem_optin = 0, smem_sm = 0;
+  cudaGetDevice(&dev);
+  cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+  cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
+  int vec = cfg.vec;
+  if (vec == 0) {
+    for (int v : {4, 2, 1})
+      if ((int)bp_smem_bytes(v, E, m, n, mw, nw) <= smem_optin) { vec = v; break; }
+    if (vec == 0) { *why = kNoFit; return false; }
+  } else if (!(vec == 1 || vec == 2 || vec == 4) || (int)bp_smem_bytes(vec, E, m, n, mw, nw) > smem_optin) {
+    *why = kBadCfg;
+    return false;
+  }
+  const int smem = (int)bp_smem_bytes(vec, E, m, n, mw, nw);
+  BpKernel k = lookup_kernel(dc, dv, vec);
+  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    cudaGetLastError();
+    *why = kNoFit;
+    return false;
+  }
+  cudaFuncAttributes fa;
+  cudaFuncGetAttributes(&fa, k);
+  int threads = cfg.threads;
+  if (threads == 0) {
+    // Each phase hands one node to a thread; pick the warp count that wastes the fewest warp-rounds over the
+    // check phase (ceil(m/32) warp-tasks) and the variable phase (ceil(n/32)), preferring 4-5 warps so that
+    // several CTAs share an SM and hide each other's barriers.
+    const int wc = (m + 31) / 32, wv = (n + 31) / 32;
+    const int smem_ctas = std::max(1, smem_sm / (smem + 1024));
+    double best = 1e30;
+    for (int w = 2; w <= kMaxT / 32; ++w) {
+      const double waste = (double)((wc + w - 1) / w * w - wc) * dc + (double)((wv + w - 1) / w * w - wv) * dv * 2;
+      const double work = (double)wc * dc + (double)wv * dv * 2;
+      const int resident = std::min(smem_ctas, std::max(1, 768 / (32 * w))) * w;  // warps per SM
+      const double occ_pen = resident >= 16 ? 0.0 : (16 - resident) * 0.03;
+      const double score = waste / work + occ_pen + 0.002 * std::abs(w - 5);
+      if (score < best) { best = score; threads = 32 * w; }
+    }
+  }
+  if (threads % 32 || threads < 32 || threads > kMaxT) { *why = kBadCfg; return false; }
+  int occ = 0;
+  if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem) != cudaSuccess || occ < 1) {
+    cudaGetLastError();
+    *why = kNoFit;
+    return false;
+  }
+  if (cfg.ctas_per_sm > 0) occ = std::min(occ, cfg.ctas_per_sm);
+  cfg.vec = vec;
+  cfg.threads = threads;
+  cfg.ctas_per_sm = occ;
+  cfg.grid = occ * num_sms;
+  cfg.smem = smem;
+  cfg.regs = fa.numRegs;
+  cfg.max_threads = kMaxT;
+  return true;
+}
+
+cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, cudaStream_t st) {
+  BpKernel k = lookup_kernel(dc, dv, cfg.vec);
+  if (!k) return cudaErrorInvalidDeviceFunction;
+  const int tiles = (nframes + cfg.vec - 1) / cfg.vec;
+  const int grid = std::max(1, std::min(cfg.grid, tiles));
+  k<<<grid, cfg.threads, cfg.smem, st>>>(args);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Error generation: device-side counter-based Philox depolarizing noise (replaces the mt19937 weight-W
+// generator of DecoderCPU.h:394-396,446-459 / RandomErrorGenerator.h:31-44 for the Monte-Carlo path).
+// One warp per frame; lane b handles Philox block b (qubits 4b..4b+3); eight lanes assemble one 32-bit word.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) generate_kernel(uint64_t seed, uint64_t first_frame, int nframes, int n, int nw,
+                                                       Thresholds thr, uint32_t* __restrict__ errX,
+                                                       uint32_t* __restrict__ errZ) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nblocks = (n + 3) >> 2;
+  for (int f = warp; f < nframes; f += nwarps) {
+    const uint64_t frame = first_frame + (uint64_t)f;
+    for (int b0 = 0; b0 < nblocks; b0 += 32) {
+      const int b = b0 + lane;
+      uint32_t xn = 0, zn = 0;
+      if (b < nblocks) {
+        depolarizing_block(seed, frame, (uint32_t)b, thr, xn, zn);
+        const int valid = n - 4 * b;  // qubits beyond n do not exist
+        if (valid < 4) {
+          const uint32_t mask = (1u << valid) - 1u;
+          xn &= mask;
+          zn &= mask;
+        }
+      }
+      uint32_t xv = xn << ((lane & 7) * 4), zv = zn << ((lane & 7) * 4);
+#pragma unroll
+      for (int s = 1; s < 8; s <<= 1) {
+        xv |= __shfl_xor_sync(0xffffffffu, xv, s);
+        zv |= __shfl_xor_sync(0xffffffffu, zv, s);
+      }
+      const int w = b >> 3;
+      if ((lane & 7) == 0 && w < nw) {
+        errX[(size_t)f * nw + w] = xv;
+        errZ[(size_t)f * nw + w] = zv;
+      }
+    }
+  }
+}
+
+cudaError_t launch_generate(uint64_t seed, uint64_t first_frame, int nframes, int n, int nw, Thresholds thr,
+                            uint32_t* errX, uint32_t* errZ, cudaStream_t st) {
+  if (nframes <= 0) return cudaSuccess;
+  const int blocks = std::min((nframes + 7) / 8, 148 * 16);
+  generate_kernel<<<blocks, 256, 0, st>>>(seed, first_frame, nframes, n, nw, thr, errX, errZ);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Syndrome s = H e mod 2 (Quantum_LDPC_Code::GetSyndromeX/Z, Quantum_LDPC_Code.h:94-124): XOR of the dc error
+// bits of each check instead of the reference's dense row scan.  One warp per frame, error words staged in
+// shared memory, lanes over checks, ballot packs the result.
+// =====================================================================================================
+__device__ __forceinline__ void syndrome_side(const uint32_t* __restrict__ ew, const uint16_t* __restrict__ cvar, int m,
+                                              int dc, int mw, uint32_t* __restrict__ out, int lane) {
+  for (int e0 = 0; e0 < m; e0 += 32) {
+    const int e = e0 + lane;
+    unsigned bit = 0;
+    if (e < m)
+      for (int i = 0; i < dc; ++i) {
+        const int v = cvar[i * m + e];
+        bit ^= (ew[v >> 5] >> (v & 31)) & 1u;
+      }
+    const unsigned w = __ballot_sync(0xffffffffu, bit);
+    if (lane == 0 && (e0 >> 5) < mw) out[e0 >> 5] = w;
+  }
+}
+
+__global__ void __launch_bounds__(256) syndrome_kernel(const uint32_t* __restrict__ errX, const uint32_t* __restrict__ errZ,
+                                                       int nframes, int n, int nw, const uint16_t* __restrict__ cvarX,
+                                                       int mX, int dcX, int mwX, uint32_t* __restrict__ synX,
+                                                       const uint16_t* __restrict__ cvarZ, int mZ, int dcZ, int mwZ,
+                                                       uint32_t* __restrict__ synZ) {
+  extern __shared__ uint32_t sh[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  uint32_t* ex = sh + (size_t)wib * 2 * nw;
+  uint32_t* ez = ex + nw;
+  for (int f = warp; f < nframes; f += nwarps) {
+    for (int w = lane; w < nw; w += 32) {
+      ex[w] = errX[(size_t)f * nw + w];
+      ez[w] = errZ[(size_t)f * nw + w];
+    }
+    __syncwarp();
+    syndrome_side(ex, cvarX, mX, dcX, mwX, synX + (size_t)f * mwX, lane);
+    syndrome_side(ez, cvarZ, mZ, dcZ, mwZ, synZ + (size_t)f * mwZ, lane);
+    __syncwarp();
+  }
+  (void)n;
+}
+
+cudaError_t launch_syndrome(const uint32_t* errX, const uint32_t* errZ, int nframes, int n, int nw,
+                            const uint16_t* cvarX, int mX, int dcX, int mwX, uint32_t* synX, const uint16_t* cvarZ,
+                            int mZ, int dcZ, int mwZ, uint32_t* synZ, cudaStream_t st) {
+  if (nframes <= 0) return cudaSuccess;
+  const int blocks = std::min((nframes + 7) / 8, 148 * 16);
+  const size_t sh = (size_t)8 * 2 * nw * sizeof(uint32_t);
+  syndrome_kernel<<<blocks, 256, sh, st>>>(errX, errZ, nframes, n, nw, cvarX, mX, dcX, mwX, synX, cvarZ, mZ, dcZ, mwZ,
+                                           synZ);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Bit pack / unpack between one-element-per-bit rows (the reference's int / byte vectors) and packed words
+// =====================================================================================================
+template <typename T>
+__global__ void __launch_bounds__(256) pack_kernel(const T* __restrict__ src, int64_t rows, int cols, int words,
+                                                   uint32_t* __restrict__ dst) {
+  const int lane = threadIdx.x & 31;
+  const int64_t warp = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int64_t nwarps = ((int64_t)gridDim.x * blockDim.x) >> 5;
+  const int64_t total = rows * words;
+  for (int64_t t = warp; t < total; t += nwarps) {
+    const int64_t r = t / words;
+    const int w = (int)(t - r * words);
+    const int c = w * 32 + lane;
+    const unsigned bit = c < cols ? (unsigned)(src[r * cols + c] != 0) : 0u;
+    const unsigned word = __ballot_sync(0xffffffffu, bit);
+    if (lane == 0) dst[t] = word;
+  }
+}
+
+__global__ void __launch_bounds__(256) unpack_kernel(const uint32_t* __restrict__ src, int64_t rows, int cols, int words,
+                                                     uint8_t* __restrict__ dst) {
+  const int64_t total = rows * cols;
+  for (int64_t t = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (int64_t)gridDim.x * blockDim.x) {
+    const int64_t r = t / cols;
+    const int c = (int)(t - r * cols);
+    dst[t] = (uint8_t)((src[r * words + (c >> 5)] >> (c & 31)) & 1u);
+  }
+}
+
+cudaError_t launch_pack(const void* src, int elem_size, int64_t rows, int cols, int words, uint32_t* dst, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  const int blocks = (int)std::min<int64_t>((rows * words + 7) / 8, 148 * 32);
+  if (elem_size == 1) pack_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)src, rows, cols, words, dst);
+  else pack_kernel<int32_t><<<blocks, 256, 0, st>>>((const int32_t*)src, rows, cols, words, dst);
+  return cudaGetLastError();
+}
+
+cudaError_t launch_unpack(const uint32_t* src, int64_t rows, int cols, int words, uint8_t* dst, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  const int blocks = (int)std::min<int64_t>((rows * cols + 255) / 256, 148 * 32);
+  unpack_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, words, dst);
+  return cudaGetLastError();
+}
+
+// =====================================================================================================
+// Statistics: the per-frame bookkeeping of GetStatistics (DecoderCPU.h:461-521) and the CodeStatistics counters
+// (CodeStatistics.h:5-20) as a warp-aggregated on-device reduction.  One warp per frame.
+// Logical check = CheckLogicalError (Quantum_LDPC_Code.h:126-142) on the residual [x^xhat | z^zhat] with
+// bit-packed, transposed rows (lane = row, coalesced), skipped when the residual is zero.
+// =====================================================================================================
+__device__ __forceinline__ bool any_odd_row(const uint32_t* __restrict__ LT, int rows, const uint32_t* r, int words,
+                                            int lane) {
+  const int rows_pad = (rows + 31) & ~31;
+  for (int g = 0; g < rows; g += 32) {
+    uint32_t acc = 0;
+    for (int w = 0; w < words; ++w) acc ^= LT[(size_t)w * rows_pad + g + lane] & r[w];
+    if (__any_sync(0xffffffffu, __popc(acc) & 1)) return true;
+  }
+  return false;
+}
+
+__global__ void __launch_bounds__(256) stats_kernel(const StatsArgs a) {
+  extern __shared__ uint32_t sh[];
+  __shared__ unsigned long long blk[QLDPC_NUM_COUNTERS];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int nw = a.nw;
+  uint32_t* res = sh + (size_t)wib * 2 * nw;  // residual words: x part, z part
+  if (threadIdx.x < QLDPC_NUM_COUNTERS) blk[threadIdx.x] = 0ull;
+  __syncthreads();
+  unsigned long long k[QLDPC_NUM_COUNTERS];
+#pragma unroll
+  for (int i = 0; i < QLDPC_NUM_COUNTERS; ++i) k[i] = 0ull;
+  for (int f = warp; f < a.nframes; f += nwarps) {
+    unsigned ex = 0, ez = 0, rx = 0, rz = 0;
+    for (int w = lane; w < nw; w += 32) {
+      const uint32_t x = a.errX[(size_t)f * nw + w], z = a.errZ[(size_t)f * nw + w];
+      const uint32_t dx = x ^ a.decX[(size_t)f * nw + w], dz = z ^ a.decZ[(size_t)f * nw + w];
+      res[w] = dx;
+      res[nw + w] = dz;
+      ex |= x; ez |= z; rx |= dx; rz |= dz;
+    }
+    __syncwarp();
+    const bool anyx = __any_sync(0xffffffffu, ex != 0), anyz = __any_sync(0xffffffffu, ez != 0);
+    const bool resx = __any_sync(0xffffffffu, rx != 0), resz = __any_sync(0xffffffffu, rz != 0);
+    const unsigned sx = a.sfX[f], sz = a.sfZ[f];
+    const bool synx = sx & 1u, synz = sz & 1u;
+    unsigned fl = (sx & 1u) | ((sz & 1u) << 1) | (((sx >> 1) & 1u) << 2) | (((sz >> 1) & 1u) << 3);
+    const bool nan = ((sx | sz) >> 2) & 1u;
+    bool logical = false, corrected = false;
+    if (!(synx || synz)) {  // DecoderCPU.h:492
+      if (resx && a.lx_rows) logical = any_odd_row(a.lx, a.lx_rows, res, nw, lane);
+      if (!logical && resz && a.lz_rows) logical = any_odd_row(a.lz, a.lz_rows, res + nw, nw, lane);
+      if (!logical && (resx || resz) && a.lm_rows) logical = any_odd_row(a.lm, a.lm_rows, res, 2 * nw, lane);
+      corrected = !logical;
+    }
+    fl |= (logical ? QLDPC_FRAME_LOGICAL : 0) | (corrected ? QLDPC_FRAME_CORRECTED : 0) | (nan ? QLDPC_FRAME_NAN : 0);
+    if (lane == 0) {
+      k[QLDPC_C_FRAMES] += 1;
+      k[QLDPC_C_XTESTED] += anyx;  // DecoderCPU.h:464-473
+      k[QLDPC_C_ZTESTED] += anyz;
+      k[QLDPC_C_CORRECTED] += corrected;
+      k[QLDPC_C_SYNX] += synx;
+      k[QLDPC_C_SYNZ] += synz;
+      k[QLDPC_C_LOGICAL] += logical;
+      k[QLDPC_C_CVX] += (sx >> 1) & 1u;  // counted independently of the outcome, DecoderCPU.h:514-521
+      k[QLDPC_C_CVZ] += (sz >> 1) & 1u;
+      k[QLDPC_C_ITERSX] += a.itX[f];
+      k[QLDPC_C_ITERSZ] += a.itZ[f];
+      k[QLDPC_C_NANFRAMES] += nan;
+      if (a.fflags) a.fflags[f] = (uint8_t)fl;
+    }
+    __syncwarp();
+  }
+  if (lane == 0) {
+#pragma unroll
+    for (int i = 0; i < QLDPC_NUM_COUNTERS; ++i)
+      if (k[i]) atomicAdd(&blk[i], k[i]);
+  }
+  __syncthreads();
+  if (threadIdx.x < QLDPC_NUM_COUNTERS && blk[threadIdx.x]) atomicAdd(&a.counters[threadIdx.x], blk[threadIdx.x]);
+}
+
+cudaError_t launch_stats(const StatsArgs& a, cudaStream_t st) {
+  if (a.nframes <= 0) return cudaSuccess;
+  const int blocks = std::min((a.nframes + 7) / 8, 148 * 8);
+  const size_t sh = (size_t)8 * 2 * a.nw * sizeof(uint32_t);
+  stats_kernel<<<blocks, 256, sh, st>>>(a);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) merge_flags_kernel(const uint8_t* __restrict__ sfX, const uint8_t* __restrict__ sfZ,
+                                                          int nframes, uint8_t* __restrict__ out) {
+  for (int f = blockIdx.x * blockDim.x + threadIdx.x; f < nframes; f += gridDim.x * blockDim.x) {
+    const unsigned sx = sfX[f], sz = sfZ[f];
+    out[f] = (uint8_t)((sx & 1u) | ((sz & 1u) << 1) | (((sx >> 1) & 1u) << 2) | (((sz >> 1) & 1u) << 3));
+  }
+}
+
+cudaError_t launch_merge_flags(const uint8_t* sfX, const uint8_t* sfZ, int nframes, uint8_t* out, cudaStream_t st) {
+  if (nframes <= 0) return cudaSuccess;
+  merge_flags_kernel<<<std::min((nframes + 255) / 256, 148 * 8), 256, 0, st>>>(sfX, sfZ, nframes, out);
+  return cudaGetLastError();
+}
+
+}  // namespace qldpc

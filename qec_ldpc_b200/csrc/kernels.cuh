@@ -1,0 +1,51 @@
+// Launch interface of the device code (kernels.cu) used by the host decoder (decoder.cu).
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+#include "bp_kernel.cuh"
+#include "philox.cuh"
+
+namespace qldpc {
+
+struct BpLaunch {
+  int vec = 0;       // frame slots per CTA tile
+  int threads = 0;   // threads per CTA
+  int ctas_per_sm = 0;
+  int grid = 0;
+  int smem = 0;      // dynamic shared memory per CTA
+  int regs = 0;
+  int max_threads = 0;
+};
+
+// Picks a kernel instantiation for (dc, dv), sizes the tile and fills `cfg` (zero fields = heuristic).
+// Returns false if no compiled instantiation covers the shape or the tile does not fit in shared memory.
+bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, const char** why);
+cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, cudaStream_t st);
+
+// Philox depolarizing errors, bit-packed: errX, errZ [nframes][nw].
+cudaError_t launch_generate(uint64_t seed, uint64_t first_frame, int nframes, int n, int nw, Thresholds thr,
+                            uint32_t* errX, uint32_t* errZ, cudaStream_t st);
+// s = H e (mod 2) for both sides from bit-packed errors; cvar tables [dc][m] per side.
+cudaError_t launch_syndrome(const uint32_t* errX, const uint32_t* errZ, int nframes, int n, int nw,
+                            const uint16_t* cvarX, int mX, int dcX, int mwX, uint32_t* synX,
+                            const uint16_t* cvarZ, int mZ, int dcZ, int mwZ, uint32_t* synZ, cudaStream_t st);
+// rows of `bits` one-per-element (elem_size 1 or 4 bytes) <-> bit-packed words
+cudaError_t launch_pack(const void* src, int elem_size, int64_t rows, int cols, int words, uint32_t* dst, cudaStream_t st);
+cudaError_t launch_unpack(const uint32_t* src, int64_t rows, int cols, int words, uint8_t* dst, cudaStream_t st);
+
+struct StatsArgs {
+  const uint32_t *errX, *errZ, *decX, *decZ;  // [nframes][nw]
+  const uint8_t *sfX, *sfZ;                   // per-side flags from the BP kernel
+  const uint32_t *itX, *itZ;
+  // logical check rows, transposed and padded to a multiple of 32 rows: LT[w][rows_pad]
+  const uint32_t *lx, *lz, *lm;
+  int lx_rows, lz_rows, lm_rows;
+  int nframes, nw;
+  unsigned long long* counters;  // [QLDPC_NUM_COUNTERS]
+  uint8_t* fflags;               // [nframes] final per-frame flags (may be null)
+};
+cudaError_t launch_stats(const StatsArgs& a, cudaStream_t st);
+// ErrorCode bits only (decode_batch): flags[f] = synX | synZ<<1 | cvX<<2 | cvZ<<3
+cudaError_t launch_merge_flags(const uint8_t* sfX, const uint8_t* sfZ, int nframes, uint8_t* out, cudaStream_t st);
+
+}  // namespace qldpc
