@@ -159,6 +159,24 @@ int qldpc_get_stats_from_errors_u8(qldpc_decoder* dec, const uint8_t* xErrors, c
                                    int64_t numErrors, float errorProbability, int maxIterations, uint64_t* counters,
                                    uint8_t* perFrameFlags, uint32_t* perFrameIters);
 
+/* ---- measurement -------------------------------------------------------------------------------------- */
+
+/* Per-kernel device timing with CUDA events on the launching stream (off by default: enabling it adds two
+ * event records per launch).  Kernel classes: */
+enum {
+  QLDPC_T_GENERATE = 0, /* Philox error generator                 */
+  QLDPC_T_SYNDROME = 1, /* sparse syndrome                        */
+  QLDPC_T_BP_X = 2,     /* BP tile kernel, X side                 */
+  QLDPC_T_BP_Z = 3,     /* BP tile kernel, Z side                 */
+  QLDPC_T_STATS = 4,    /* residual / logical check / counters    */
+  QLDPC_T_PACK = 5,     /* pack / unpack / flag merge             */
+  QLDPC_NUM_TIMERS = 6
+};
+int qldpc_decoder_enable_timing(qldpc_decoder* dec, int on);
+/* Accumulated since the last reset: ms[QLDPC_NUM_TIMERS] device milliseconds and launches[QLDPC_NUM_TIMERS]
+ * kernel launches per class (launches are counted whether or not timing is enabled).  reset != 0 clears them. */
+int qldpc_decoder_get_timing(qldpc_decoder* dec, double* ms, uint64_t* launches, int reset);
+
 /* ---- parity taps (tests) ------------------------------------------------------------------------------- */
 
 /* Device Philox generator + syndrome kernel, unpacked to host bytes: xerr, zerr [nframes x n],

@@ -199,6 +199,14 @@ void oracle_depolarizing(const oracle_code* c, uint64_t seed, uint64_t frame, fl
   }
 }
 
+/* [nframes x n] byte patterns for frames first_frame .. first_frame+nframes-1 (OpenMP over frames). */
+void oracle_depolarizing_bulk(const oracle_code* c, uint64_t seed, uint64_t first_frame, int nframes, float p,
+                              uint8_t* xerr, uint8_t* zerr) {
+#pragma omp parallel for schedule(static)
+  for (int f = 0; f < nframes; ++f)
+    oracle_depolarizing(c, seed, first_frame + (uint64_t)f, p, xerr + (size_t)f * c->n, zerr + (size_t)f * c->n);
+}
+
 /* ------------------------------------------------------------------------------------------------
  * Weight-W compatibility generator: std::mt19937 + MSVC's uniform_int_distribution mapping, drawn in the
  * order index, type, W times per frame, frames in sequence.  DecoderCPU.h:394-396, :449-458.

@@ -33,6 +33,9 @@ void oracle_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t
 void oracle_depolarizing_thresholds(float p, uint32_t t[3]);
 void oracle_depolarizing(const oracle_code* c, uint64_t seed, uint64_t frame, float p, uint8_t* xerr, uint8_t* zerr);
 
+void oracle_depolarizing_bulk(const oracle_code* c, uint64_t seed, uint64_t first_frame, int nframes, float p,
+                              uint8_t* xerr, uint8_t* zerr);
+
 void oracle_syndrome(const oracle_code* c, int side, const uint8_t* err, uint8_t* syn);
 int oracle_bp(const oracle_code* c, int side, const uint8_t* syn, float errorProbability, int maxIterations, float* q,
               float* r, float* q_trace, float* r_trace, int trace_cap);

@@ -59,6 +59,7 @@ class Oracle:
         L.oracle_philox4x32_10.argtypes = [u32p, u32p, u32p]
         L.oracle_depolarizing_thresholds.argtypes = [C.c_float, u32p]
         L.oracle_depolarizing.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_float, u8p, u8p]
+        L.oracle_depolarizing_bulk.argtypes = [C.c_void_p, C.c_uint64, C.c_uint64, C.c_int, C.c_float, u8p, u8p]
         L.oracle_syndrome.argtypes = [C.c_void_p, C.c_int, u8p, u8p]
         L.oracle_bp.restype = C.c_int
         L.oracle_bp.argtypes = [C.c_void_p, C.c_int, u8p, C.c_float, C.c_int, f32p, f32p, C.c_void_p, C.c_void_p, C.c_int]
@@ -150,6 +151,11 @@ class OracleCode:
     def depolarizing(self, seed, frame, p):
         x, z = np.zeros(self.n, np.uint8), np.zeros(self.n, np.uint8)
         self.L.oracle_depolarizing(self.h, seed, frame, p, x, z)
+        return x, z
+
+    def depolarizing_bulk(self, seed, first_frame, nframes, p):
+        x, z = np.zeros((nframes, self.n), np.uint8), np.zeros((nframes, self.n), np.uint8)
+        self.L.oracle_depolarizing_bulk(self.h, seed, first_frame, nframes, p, x, z)
         return x, z
 
     def syndrome(self, side, err):

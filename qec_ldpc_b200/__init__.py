@@ -76,6 +76,8 @@ def load_library():
     L.qldpc_get_statistics_depolarizing.argtypes = [vp, u64, u64, i64, f32, i32, vp, vp, vp]
     L.qldpc_get_stats_from_errors_i32.argtypes = [vp, vp, vp, i64, f32, i32, vp, vp, vp]
     L.qldpc_get_stats_from_errors_u8.argtypes = [vp, vp, vp, i64, f32, i32, vp, vp, vp]
+    L.qldpc_decoder_enable_timing.argtypes = [vp, i32]
+    L.qldpc_decoder_get_timing.argtypes = [vp, vp, vp, i32]
     L.qldpc_debug_generate.argtypes = [vp, u64, u64, i64, f32, vp, vp, vp, vp]
     L.qldpc_debug_bp_trace.argtypes = [vp, i32, vp, i32, f32, i32, i32, vp, vp, vp]
     _lib = L
@@ -213,6 +215,17 @@ class Decoder:
         _check(self._lib.qldpc_decoder_launch_info(self.h, side, _ptr(out)))
         keys = ["vec", "threads", "ctas_per_sm", "grid", "smem", "regs", "num_sms", "chunk"]
         return dict(zip(keys, [int(v) for v in out]))
+
+    TIMER_NAMES = ["generate", "syndrome", "bp_x", "bp_z", "stats", "pack"]
+
+    def enable_timing(self, on=True):
+        _check(self._lib.qldpc_decoder_enable_timing(self.h, int(on)))
+
+    def get_timing(self, reset=True):
+        ms = np.zeros(6, np.float64)
+        n = np.zeros(6, np.uint64)
+        _check(self._lib.qldpc_decoder_get_timing(self.h, _ptr(ms), _ptr(n), int(reset)))
+        return dict(zip(self.TIMER_NAMES, ms.tolist())), dict(zip(self.TIMER_NAMES, [int(v) for v in n]))
 
     def decode_batch(self, synX, synZ, p, maxit, want_iters=True):
         sx = np.ascontiguousarray(synX, np.uint8)

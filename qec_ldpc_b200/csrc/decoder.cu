@@ -71,6 +71,13 @@ struct qldpc_decoder {
   size_t stage_bytes = 0;
   uint32_t* pin = nullptr;  // pinned host staging for the weight-W generator
   size_t pin_words = 0;
+  // measurement: launches per kernel class, and (when enabled) CUDA-event pairs on the launching stream
+  bool timing = false;
+  uint64_t launches[QLDPC_NUM_TIMERS] = {0, 0, 0, 0, 0, 0};
+  double ms[QLDPC_NUM_TIMERS] = {0, 0, 0, 0, 0, 0};
+  struct Pending { int cls; cudaEvent_t a, b; };
+  std::vector<Pending> pending;
+  std::vector<cudaEvent_t> pool;
 
   ~qldpc_decoder() {
     cudaSetDevice(device);
@@ -79,11 +86,49 @@ struct qldpc_decoder {
     cudaFree(sfX); cudaFree(sfZ); cudaFree(fflags); cudaFree(itX); cudaFree(itZ);
     cudaFree(counters); cudaFree(queues); cudaFree(lx); cudaFree(lz); cudaFree(lm); cudaFree(stage);
     if (pin) cudaFreeHost(pin);
+    for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
+    for (auto e : pool) cudaEventDestroy(e);
     if (own_stream) cudaStreamDestroy(own_stream);
   }
 };
 
 namespace {
+
+// Counts a launch of kernel class `cls`; with timing enabled brackets it with events on the launch stream.
+struct Timed {
+  qldpc_decoder* d;
+  int cls;
+  cudaEvent_t a = nullptr, b = nullptr;
+  Timed(qldpc_decoder* d_, int cls_, int n = 1) : d(d_), cls(cls_) {
+    d->launches[cls] += (uint64_t)n;
+    if (!d->timing) return;
+    auto get = [&]() {
+      cudaEvent_t e = nullptr;
+      if (!d->pool.empty()) { e = d->pool.back(); d->pool.pop_back(); }
+      else cudaEventCreate(&e);
+      return e;
+    };
+    a = get();
+    b = get();
+    cudaEventRecord(a, d->stream);
+  }
+  ~Timed() {
+    if (!a) return;
+    cudaEventRecord(b, d->stream);
+    d->pending.push_back({cls, a, b});
+  }
+};
+
+void drain_timing(qldpc_decoder* d) {
+  for (auto& p : d->pending) {
+    float t = 0.f;
+    if (cudaEventSynchronize(p.b) == cudaSuccess && cudaEventElapsedTime(&t, p.a, p.b) == cudaSuccess) d->ms[p.cls] += t;
+    d->pool.push_back(p.a);
+    d->pool.push_back(p.b);
+  }
+  d->pending.clear();
+  cudaGetLastError();
+}
 
 int ensure_stage(qldpc_decoder* d, size_t bytes) {
   if (bytes <= d->stage_bytes) return QLDPC_OK;
@@ -158,6 +203,7 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
     a.maxit = maxIterations;
     a.prior = prior;
     a.trace_q = trace_q; a.trace_r = trace_r; a.trace_cap = trace_cap;
+    Timed t(d, side ? QLDPC_T_BP_Z : QLDPC_T_BP_X);
     CU_TRY(bp_launch(s.dc, s.dv, s.cfg, a, nf, d->stream));
   }
   return QLDPC_OK;
@@ -172,11 +218,13 @@ int run_stats(qldpc_decoder* d, int nf, uint8_t* fflags) {
   a.nframes = nf; a.nw = d->nw;
   a.counters = d->counters;
   a.fflags = fflags;
+  Timed t(d, QLDPC_T_STATS);
   CU_TRY(launch_stats(a, d->stream));
   return QLDPC_OK;
 }
 
 int run_syndrome(qldpc_decoder* d, int nf) {
+  Timed t(d, QLDPC_T_SYNDROME);
   CU_TRY(launch_syndrome(d->errX, d->errZ, nf, d->n, d->nw, d->s[0].cvar, d->s[0].m, d->s[0].dc, d->s[0].mw, d->synX,
                          d->s[1].cvar, d->s[1].m, d->s[1].dc, d->s[1].mw, d->synZ, d->stream));
   return QLDPC_OK;
@@ -482,6 +530,24 @@ int qldpc_decoder_launch_info(qldpc_decoder* dec, int side, int32_t out[8]) {
   return QLDPC_OK;
 }
 
+int qldpc_decoder_enable_timing(qldpc_decoder* dec, int on) {
+  if (!dec) return fail(QLDPC_ERR_ARG, "null decoder");
+  dec->timing = on != 0;
+  return QLDPC_OK;
+}
+
+int qldpc_decoder_get_timing(qldpc_decoder* dec, double* ms, uint64_t* launches, int reset) {
+  if (!dec) return fail(QLDPC_ERR_ARG, "null decoder");
+  CU_TRY(cudaSetDevice(dec->device));
+  drain_timing(dec);
+  for (int i = 0; i < QLDPC_NUM_TIMERS; ++i) {
+    if (ms) ms[i] = dec->ms[i];
+    if (launches) launches[i] = dec->launches[i];
+    if (reset) { dec->ms[i] = 0; dec->launches[i] = 0; }
+  }
+  return QLDPC_OK;
+}
+
 int qldpc_decode_batch_device(qldpc_decoder* dec, const uint32_t* d_synX, const uint32_t* d_synZ, int64_t nframes,
                               float errorProbability, int maxIterations, uint32_t* d_outX, uint32_t* d_outZ,
                               uint8_t* d_outFlags, uint32_t* d_outIters) {
@@ -494,7 +560,10 @@ int qldpc_decode_batch_device(qldpc_decoder* dec, const uint32_t* d_synX, const 
     rc = run_bp(d, d_synX + off * d->s[0].mw, d_synZ + off * d->s[1].mw, nf, errorProbability, maxIterations,
                 d_outX + off * d->nw, d_outZ + off * d->nw, d->sfX, d->sfZ, d->itX, d->itZ);
     if (rc) return rc;
-    CU_TRY(launch_merge_flags(d->sfX, d->sfZ, nf, d_outFlags + off, d->stream));
+    {
+      Timed t(d, QLDPC_T_PACK);
+      CU_TRY(launch_merge_flags(d->sfX, d->sfZ, nf, d_outFlags + off, d->stream));
+    }
     if (d_outIters) {
       CU_TRY(cudaMemcpy2DAsync(d_outIters + 2 * off, 8, d->itX, 4, 4, (size_t)nf, cudaMemcpyDeviceToDevice, d->stream));
       CU_TRY(cudaMemcpy2DAsync(d_outIters + 2 * off + 1, 8, d->itZ, 4, 4, (size_t)nf, cudaMemcpyDeviceToDevice, d->stream));
@@ -521,13 +590,19 @@ int qldpc_decode_batch(qldpc_decoder* dec, const uint8_t* synX, const uint8_t* s
     uint8_t* st1 = st0 + per * nf;
     CU_TRY(cudaMemcpyAsync(st0, synX + off * mX, (size_t)nf * mX, cudaMemcpyHostToDevice, d->stream));
     CU_TRY(cudaMemcpyAsync(st1, synZ + off * mZ, (size_t)nf * mZ, cudaMemcpyHostToDevice, d->stream));
-    CU_TRY(launch_pack(st0, 1, nf, mX, d->s[0].mw, d->synX, d->stream));
-    CU_TRY(launch_pack(st1, 1, nf, mZ, d->s[1].mw, d->synZ, d->stream));
+    {
+      Timed t(d, QLDPC_T_PACK, 2);
+      CU_TRY(launch_pack(st0, 1, nf, mX, d->s[0].mw, d->synX, d->stream));
+      CU_TRY(launch_pack(st1, 1, nf, mZ, d->s[1].mw, d->synZ, d->stream));
+    }
     rc = run_bp(d, d->synX, d->synZ, nf, errorProbability, maxIterations, d->decX, d->decZ, d->sfX, d->sfZ, d->itX, d->itZ);
     if (rc) return rc;
-    CU_TRY(launch_unpack(d->decX, nf, n, d->nw, st0, d->stream));
-    CU_TRY(launch_unpack(d->decZ, nf, n, d->nw, st1, d->stream));
-    CU_TRY(launch_merge_flags(d->sfX, d->sfZ, nf, d->fflags, d->stream));
+    {
+      Timed t(d, QLDPC_T_PACK, 3);
+      CU_TRY(launch_unpack(d->decX, nf, n, d->nw, st0, d->stream));
+      CU_TRY(launch_unpack(d->decZ, nf, n, d->nw, st1, d->stream));
+      CU_TRY(launch_merge_flags(d->sfX, d->sfZ, nf, d->fflags, d->stream));
+    }
     CU_TRY(cudaMemcpyAsync(outX + off * n, st0, (size_t)nf * n, cudaMemcpyDeviceToHost, d->stream));
     CU_TRY(cudaMemcpyAsync(outZ + off * n, st1, (size_t)nf * n, cudaMemcpyDeviceToHost, d->stream));
     CU_TRY(cudaMemcpyAsync(outFlags + off, d->fflags, (size_t)nf, cudaMemcpyDeviceToHost, d->stream));
@@ -550,7 +625,10 @@ int qldpc_get_statistics_depolarizing(qldpc_decoder* dec, uint64_t seed, uint64_
   CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
   for (int64_t off = 0; off < nframes; off += d->chunk) {
     const int nf = (int)std::min<int64_t>(d->chunk, nframes - off);
-    CU_TRY(launch_generate(seed, first_frame + (uint64_t)off, nf, d->n, d->nw, thr, d->errX, d->errZ, d->stream));
+    {
+      Timed t(d, QLDPC_T_GENERATE);
+      CU_TRY(launch_generate(seed, first_frame + (uint64_t)off, nf, d->n, d->nw, thr, d->errX, d->errZ, d->stream));
+    }
     rc = run_syndrome(d, nf);
     if (rc) return rc;
     rc = finish_chunk(d, nf, off, p, maxIterations, perFrameFlags, perFrameIters);
@@ -626,8 +704,11 @@ static int stats_from_errors(qldpc_decoder* d, const void* xErrors, const void* 
     uint8_t* st1 = st0 + row * nf;
     CU_TRY(cudaMemcpyAsync(st0, (const uint8_t*)xErrors + off * row, row * nf, cudaMemcpyHostToDevice, d->stream));
     CU_TRY(cudaMemcpyAsync(st1, (const uint8_t*)zErrors + off * row, row * nf, cudaMemcpyHostToDevice, d->stream));
-    CU_TRY(launch_pack(st0, elem, nf, n, d->nw, d->errX, d->stream));
-    CU_TRY(launch_pack(st1, elem, nf, n, d->nw, d->errZ, d->stream));
+    {
+      Timed t(d, QLDPC_T_PACK, 2);
+      CU_TRY(launch_pack(st0, elem, nf, n, d->nw, d->errX, d->stream));
+      CU_TRY(launch_pack(st1, elem, nf, n, d->nw, d->errZ, d->stream));
+    }
     rc = run_syndrome(d, nf);
     if (rc) return rc;
     rc = finish_chunk(d, nf, off, errorProbability, maxIterations, perFrameFlags, perFrameIters);

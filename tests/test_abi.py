@@ -1,0 +1,49 @@
+"""The C-ABI library loads, exports every symbol include/qldpc_b200.h declares, and has no CPU decode path."""
+import ctypes
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def declared_symbols():
+    text = open(os.path.join(ROOT, "include", "qldpc_b200.h")).read()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(qldpc_[a-z0-9_]+)\s*\(", text)))
+
+
+def test_header_symbols_exported(qldpc):
+    lib = ctypes.CDLL(qldpc.LIB_PATH)
+    names = declared_symbols()
+    assert len(names) >= 25
+    for n in names:
+        assert hasattr(lib, n), "missing export " + n
+
+
+def test_header_cites_reference_interfaces():
+    text = open(os.path.join(ROOT, "include", "qldpc_b200.h")).read()
+    for cite in ["Decoder.h:40", "DecoderCPU.h:392", "DecoderGPU.h:193", "Quantum_LDPC_Code.h:26", "QEC_LDPC_CSS.cu:37"]:
+        assert cite in text
+
+
+def test_no_gpu_fails_loudly(qldpc):
+    """Without a CUDA device the decoder refuses to exist: no silent CPU fallback."""
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("a GPU is present")
+    code = qldpc.Code.qc(3, 3, 6, 7, 2, 3)
+    with pytest.raises(qldpc.QldpcError) as e:
+        qldpc.Decoder(code)
+    assert e.value.code == qldpc.ERR_NO_DEVICE
+
+
+def test_product_does_not_touch_oracle():
+    """The product package must not import, link or execute anything under oracle/."""
+    pkg = os.path.join(ROOT, "qec_ldpc_b200")
+    for base, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
+                src = open(os.path.join(base, f), errors="ignore").read()
+                assert "pyoracle" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/oracle.c restates", ""), f
