@@ -190,6 +190,11 @@ int qldpc_debug_generate(qldpc_decoder* dec, uint64_t seed, uint64_t first_frame
 int qldpc_debug_bp_trace(qldpc_decoder* dec, int side, const uint8_t* syn, int nframes, float errorProbability,
                          int maxIterations, int cap_iters, float* q_trace, float* r_trace, uint32_t* iters);
 
+/* Checks the branch-free division used by the BP kernel against IEEE division (__fdiv_rn) on `npairs` random
+ * operand pairs 0 <= x <= y: out[0] = mismatching pairs (must be 0), out[1] = pairs the fast path defers to
+ * __fdiv_rn (tiny numerators / denormal denominators), out[2] = pairs with x == 0. */
+int qldpc_debug_division_check(qldpc_decoder* dec, uint64_t seed, int64_t npairs, uint64_t out[3]);
+
 #ifdef __cplusplus
 }
 #endif

@@ -78,6 +78,7 @@ def load_library():
     L.qldpc_get_stats_from_errors_u8.argtypes = [vp, vp, vp, i64, f32, i32, vp, vp, vp]
     L.qldpc_decoder_enable_timing.argtypes = [vp, i32]
     L.qldpc_decoder_get_timing.argtypes = [vp, vp, vp, i32]
+    L.qldpc_debug_division_check.argtypes = [vp, u64, i64, vp]
     L.qldpc_debug_generate.argtypes = [vp, u64, u64, i64, f32, vp, vp, vp, vp]
     L.qldpc_debug_bp_trace.argtypes = [vp, i32, vp, i32, f32, i32, i32, vp, vp, vp]
     _lib = L
@@ -271,6 +272,11 @@ class Decoder:
         k = np.zeros(NUM_COUNTERS, np.uint64)
         _check(fn(self.h, C.c_void_p(x_ptr), C.c_void_p(z_ptr), nframes, p, maxit, _ptr(k), None, None))
         return k
+
+    def debug_division_check(self, seed, npairs):
+        out = np.zeros(3, np.uint64)
+        _check(self._lib.qldpc_debug_division_check(self.h, seed, npairs, _ptr(out)))
+        return dict(mismatches=int(out[0]), deferred=int(out[1]), zero_numerators=int(out[2]))
 
     def debug_generate(self, seed, first_frame, nframes, p):
         n, mX, mZ = self.code.n, self.code.mX, self.code.mZ

@@ -798,4 +798,22 @@ int qldpc_debug_bp_trace(qldpc_decoder* dec, int side, const uint8_t* syn, int n
   return cleanup(rc);
 }
 
+int qldpc_debug_division_check(qldpc_decoder* dec, uint64_t seed, int64_t npairs, uint64_t out[3]) {
+  if (!dec || !out || npairs < 0) return fail(QLDPC_ERR_ARG, "bad argument");
+  CU_TRY(cudaSetDevice(dec->device));
+  unsigned long long* d = nullptr;
+  CU_TRY(dev_alloc(d, (size_t)3));
+  int rc = [&]() -> int {
+    CU_TRY(cudaMemsetAsync(d, 0, 3 * sizeof(unsigned long long), dec->stream));
+    CU_TRY(launch_division_check(seed, (long long)npairs, d, dec->stream));
+    unsigned long long h[3];
+    CU_TRY(cudaMemcpyAsync(h, d, sizeof h, cudaMemcpyDeviceToHost, dec->stream));
+    CU_TRY(cudaStreamSynchronize(dec->stream));
+    for (int i = 0; i < 3; ++i) out[i] = (uint64_t)h[i];
+    return QLDPC_OK;
+  }();
+  cudaFree(d);
+  return rc;
+}
+
 }  // extern "C"

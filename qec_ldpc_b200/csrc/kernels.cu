@@ -370,4 +370,44 @@ cudaError_t launch_merge_flags(const uint8_t* sfX, const uint8_t* sfZ, int nfram
   return cudaGetLastError();
 }
 
+
+// =====================================================================================================
+// Parity tap for div_fast (bp_kernel.cuh): random operand pairs 0 <= x <= y from Philox, wide exponent spread,
+// compared bit for bit with __fdiv_rn wherever div_fast does not flag the pair as unsafe.
+// =====================================================================================================
+__global__ void __launch_bounds__(256) division_check_kernel(uint64_t seed, long long npairs, unsigned long long* out) {
+  unsigned long long mism = 0, unsafe_n = 0, zero_n = 0;
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < npairs; i += stride) {
+    uint32_t r[4];
+    philox4x32_10((uint32_t)i, (uint32_t)(i >> 32), 0x44495631u, 0u, (uint32_t)seed, (uint32_t)(seed >> 32), r);
+    // y: random mantissa, exponent in [2^-104, 2^1]; x = y scaled down by a random factor in (0, 1], or 0, or y
+    const uint32_t ey = 23u + r[2] % 106u;                       // biased exponent 23..128
+    const float y = __uint_as_float((ey << 23) | (r[0] & 0x7FFFFFu));
+    float x;
+    const uint32_t sel = r[3] & 15u;
+    if (sel == 0) x = 0.0f;
+    else if (sel == 1) x = y;
+    else {
+      const uint32_t ex = 1u + (r[3] >> 4) % ey;                 // biased exponent 1..ey
+      x = __uint_as_float((ex << 23) | (r[1] & 0x7FFFFFu));
+      if (x > y) x = y;
+    }
+    bool unsafe = false;
+    const float q = div_fast(x, y, unsafe);
+    const float want = __fdiv_rn(x, y);
+    if (unsafe) ++unsafe_n;
+    else if (__float_as_uint(q) != __float_as_uint(want)) ++mism;
+    if (x == 0.0f) ++zero_n;
+  }
+  atomicAdd(&out[0], mism);
+  atomicAdd(&out[1], unsafe_n);
+  atomicAdd(&out[2], zero_n);
+}
+
+cudaError_t launch_division_check(uint64_t seed, long long npairs, unsigned long long* out, cudaStream_t st) {
+  division_check_kernel<<<148 * 8, 256, 0, st>>>(seed, npairs, out);
+  return cudaGetLastError();
+}
+
 }  // namespace qldpc

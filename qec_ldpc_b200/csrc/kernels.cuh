@@ -48,4 +48,7 @@ cudaError_t launch_stats(const StatsArgs& a, cudaStream_t st);
 // ErrorCode bits only (decode_batch): flags[f] = synX | synZ<<1 | cvX<<2 | cvZ<<3
 cudaError_t launch_merge_flags(const uint8_t* sfX, const uint8_t* sfZ, int nframes, uint8_t* out, cudaStream_t st);
 
+// out[3] = {mismatches vs __fdiv_rn among pairs div_fast accepts, pairs flagged unsafe, pairs with x == 0}
+cudaError_t launch_division_check(uint64_t seed, long long npairs, unsigned long long* out, cudaStream_t st);
+
 }  // namespace qldpc

@@ -270,3 +270,12 @@ def test_fer_matches_oracle_within_confidence(oracle, decoders):
     f_cpu, f_gpu = 1 - int(b[3]) / n_cpu, 1 - int(a[3]) / n_gpu
     sigma = np.sqrt(f_gpu * (1 - f_gpu) * (1 / n_cpu + 1 / n_gpu))
     assert abs(f_cpu - f_gpu) < 5 * sigma
+
+
+def test_division_fast_path_is_correctly_rounded(decoders):
+    """The BP kernel's branch-free division equals IEEE division (__fdiv_rn) on 2^28 random pairs 0 <= x <= y spanning
+    106 binades, including x == 0 and x == y; only tiny numerators are deferred to __fdiv_rn itself."""
+    _, dec = decoders("C1")
+    r = dec.debug_division_check(20261018, 1 << 28)
+    assert r["mismatches"] == 0
+    assert r["zero_numerators"] > (1 << 28) // 20 and 0 < r["deferred"] < (1 << 28) // 2
