@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <cmath>
 #include <cstdio>
 #include <cstring>
 #include <random>
@@ -179,6 +180,21 @@ int resolve_config(qldpc_decoder* d, int side) {
   return QLDPC_OK;
 }
 
+// Which range tests the kernel's branch-free division needs outside the `last` iteration (bp_kernel.cuh:div_fast).
+// A numerator is prior * (dv-1 check-to-variable messages), each 0 or >= 2^-25; a denominator adds
+// (1-prior) * (dv-1 complements), each 0 or >= 2^-24.  If the smallest non-zero value already clears the
+// threshold the test can never fire and is compiled out.
+int division_guard(float prior, int dv) {
+  if (!(prior > 0.0f && prior < 1.0f)) return 3;
+  const int nf = dv - 1;
+  const double xmin = std::ldexp((double)prior, -25 * nf);
+  const double ymin = std::min(xmin, std::ldexp(1.0 - (double)prior, -24 * nf));
+  int g = 0;
+  if (xmin < std::ldexp(1.0, -100)) g |= 1;
+  if (ymin < std::ldexp(1.0, -126)) g = 3;
+  return g;
+}
+
 // BP on both sides over nf frames whose bit-packed syndromes are resident on the device.
 int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf, float errorProbability, int maxIterations,
            uint32_t* decX, uint32_t* decZ, uint8_t* sfX, uint8_t* sfZ, uint32_t* itX, uint32_t* itZ, int only_side = -1,
@@ -196,7 +212,6 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
     a.flags = side ? sfZ : sfX;
     a.iters = side ? itZ : itX;
     a.vrow = s.vrow;
-    a.cvar = s.cvar;
     a.queue = d->queues + side;
     a.m = s.m; a.n = d->n; a.mw = s.mw; a.nw = d->nw;
     a.nframes = nf;
@@ -204,7 +219,7 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
     a.prior = prior;
     a.trace_q = trace_q; a.trace_r = trace_r; a.trace_cap = trace_cap;
     Timed t(d, side ? QLDPC_T_BP_Z : QLDPC_T_BP_X);
-    CU_TRY(bp_launch(s.dc, s.dv, s.cfg, a, nf, d->stream));
+    CU_TRY(bp_launch(s.dc, s.dv, s.cfg, a, nf, division_guard(prior, s.dv), d->stream));
   }
   return QLDPC_OK;
 }

@@ -13,36 +13,19 @@ namespace qldpc {
 // BP dispatch
 // =====================================================================================================
 
-// Register budget: (MAXT, MINB) = (256, 2) lets the compiler use up to 128 registers; the tile kernels need
-// well under 100, which leaves 640+ resident threads per SM next to the shared-memory limit.
-constexpr int kMaxT = 256;
-constexpr int kMinB = 2;
-
 typedef void (*BpKernel)(const BpArgs);
+constexpr int kMaxT = 256;
+// one translation unit per shape (bp_shape_<dc>_<dv>.cu)
+#define QLDPC_SHAPES(X) X(6, 3) X(10, 4) X(10, 5) X(8, 4) X(8, 3) X(12, 6)
+#define QLDPC_DECL(DC, DV) BpKernel bp_shape_##DC##_##DV(int vec, int guard);
+QLDPC_SHAPES(QLDPC_DECL)
+#undef QLDPC_DECL
 
-template <int DC, int DV>
-static BpKernel kernel_for_vec(int vec) {
-  switch (vec) {
-    case 4: return bp_tile_kernel<DC, DV, 4, kMaxT, kMinB>;
-    case 2: return bp_tile_kernel<DC, DV, 2, kMaxT, kMinB>;
-    case 1: return bp_tile_kernel<DC, DV, 1, kMaxT, kMinB>;
-  }
-  return nullptr;
-}
-
-static BpKernel lookup_kernel(int dc, int dv, int vec) {
-#define QLDPC_SHAPE(DC, DV) \
-  if (dc == DC && dv == DV) return kernel_for_vec<DC, DV>(vec);
-  QLDPC_SHAPE(6, 3)    // J3K3L6P7 (both sides)
-  QLDPC_SHAPE(10, 4)   // J4K5L10P61 X side
-  QLDPC_SHAPE(10, 5)   // J4K5L10P61 Z side
-  QLDPC_SHAPE(8, 4)    // J4K4L8P509 (both sides)
-  QLDPC_SHAPE(4, 2)
-  QLDPC_SHAPE(6, 2)
-  QLDPC_SHAPE(8, 3)
-  QLDPC_SHAPE(12, 5)
-  QLDPC_SHAPE(12, 6)
-#undef QLDPC_SHAPE
+static BpKernel lookup_kernel(int dc, int dv, int vec, int guard) {
+#define QLDPC_CASE(DC, DV) \
+  if (dc == DC && dv == DV) return bp_shape_##DC##_##DV(vec, guard);
+  QLDPC_SHAPES(QLDPC_CASE)
+#undef QLDPC_CASE
   return nullptr;
 }
 
@@ -50,7 +33,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   static const char* kNoShape = "no compiled BP kernel for this (check degree, variable degree)";
   static const char* kNoFit = "one frame of messages does not fit in shared memory (HBM-resident variant not built)";
   static const char* kBadCfg = "invalid launch configuration";
-  if (!lookup_kernel(dc, dv, 1)) { *why = kNoShape; return false; }
+  if (!lookup_kernel(dc, dv, 1, 0)) { *why = kNoShape; return false; }
   const int E = m * dc, mw = (m + 31) / 32, nw = (n + 31) / 32;
   if (E >= 65536) { *why = kNoFit; return false; }
   int dev = 0, smem_optin = 0, smem_sm = 0;
@@ -67,14 +50,19 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
     return false;
   }
   const int smem = (int)bp_smem_bytes(vec, E, m, n, mw, nw);
-  BpKernel k = lookup_kernel(dc, dv, vec);
-  if (cudaFuncSetAttribute(k, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
-    cudaGetLastError();
-    *why = kNoFit;
-    return false;
+  int regs = 0;
+  for (int guard : {0, 1, 3}) {
+    BpKernel kg = lookup_kernel(dc, dv, vec, guard);
+    if (cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+      cudaGetLastError();
+      *why = kNoFit;
+      return false;
+    }
+    cudaFuncAttributes fa;
+    cudaFuncGetAttributes(&fa, kg);
+    regs = std::max(regs, fa.numRegs);
   }
-  cudaFuncAttributes fa;
-  cudaFuncGetAttributes(&fa, k);
+  BpKernel k = lookup_kernel(dc, dv, vec, 3);
   int threads = cfg.threads;
   if (threads == 0) {
     // Each phase hands one node to a thread; pick the warp count that wastes the fewest warp-rounds over the
@@ -105,13 +93,13 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   cfg.ctas_per_sm = occ;
   cfg.grid = occ * num_sms;
   cfg.smem = smem;
-  cfg.regs = fa.numRegs;
+  cfg.regs = regs;
   cfg.max_threads = kMaxT;
   return true;
 }
 
-cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, cudaStream_t st) {
-  BpKernel k = lookup_kernel(dc, dv, cfg.vec);
+cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, int guard, cudaStream_t st) {
+  BpKernel k = lookup_kernel(dc, dv, cfg.vec, guard);
   if (!k) return cudaErrorInvalidDeviceFunction;
   const int tiles = (nframes + cfg.vec - 1) / cfg.vec;
   const int grid = std::max(1, std::min(cfg.grid, tiles));
@@ -394,7 +382,7 @@ __global__ void __launch_bounds__(256) division_check_kernel(uint64_t seed, long
       if (x > y) x = y;
     }
     bool unsafe = false;
-    const float q = div_fast(x, y, unsafe);
+    const float q = div_fast<3>(x, y, unsafe);
     const float want = __fdiv_rn(x, y);
     if (unsafe) ++unsafe_n;
     else if (__float_as_uint(q) != __float_as_uint(want)) ++mism;

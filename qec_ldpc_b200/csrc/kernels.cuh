@@ -20,7 +20,8 @@ struct BpLaunch {
 // Picks a kernel instantiation for (dc, dv), sizes the tile and fills `cfg` (zero fields = heuristic).
 // Returns false if no compiled instantiation covers the shape or the tile does not fit in shared memory.
 bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, const char** why);
-cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, cudaStream_t st);
+// guard: division range tests compiled in (0 none, 1 numerator, 3 both), see bp_kernel.cuh:div_fast
+cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, int guard, cudaStream_t st);
 
 // Philox depolarizing errors, bit-packed: errX, errZ [nframes][nw].
 cudaError_t launch_generate(uint64_t seed, uint64_t first_frame, int nframes, int n, int nw, Thresholds thr,
