@@ -228,14 +228,10 @@ def run_native(args):
     kms, klaunch = dec.get_timing(reset=True)
     dec.enable_timing(False)
 
-    # the only collective: all-reduce of the counter vector (sum) and of the time (max over ranks)
-    t = torch.tensor([ms_total], dtype=torch.float64, device="cuda")
-    c = torch.from_numpy(counters.astype(np.int64)).cuda()
-    if world > 1:
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        dist.all_reduce(c, op=dist.ReduceOp.SUM)
-    ms_total = float(t.item())
-    gc = c.cpu().numpy()
+    # the only data collective: one NCCL all-reduce (sum) of the counter vector; the time is max-reduced over ranks
+    from qec_ldpc_b200.sharding import allreduce_counters, allreduce_max
+    ms_total = allreduce_max(ms_total, "cuda")
+    gc = allreduce_counters(counters, "cuda")
 
     # ---- end to end through the C ABI with HOST buffers ("e2e") ----------------------------------------------
     # DecoderGPU::GetStats(..., xErrors, zErrors) (DecoderGPU.h:193): pre-generated patterns in host memory, in the
@@ -258,10 +254,7 @@ def run_native(args):
         e2e_counters = dec.get_stats_from_errors_ptr(xh.data_ptr(), zh.data_ptr(), F, P, MAXIT, elem=4)
     torch.cuda.synchronize()
     e2e_s = time.perf_counter() - t0
-    te = torch.tensor([e2e_s], dtype=torch.float64, device="cuda")
-    if world > 1:
-        dist.all_reduce(te, op=dist.ReduceOp.MAX)
-    e2e_s = float(te.item())
+    e2e_s = allreduce_max(e2e_s, "cuda")
     # same patterns as step 0 of the device-resident run => same counters (checked on every rank)
     chk = dec.get_statistics_depolarizing(SEED, first_frame(0), F, P, MAXIT)["counters"]
     assert np.array_equal(chk, e2e_counters), "host-buffer path and device-generated path disagree"

@@ -82,6 +82,9 @@ def main():
         rec["code"] = code
         rec["errorProbability"] = p
         rec["source"] = path[len(REF) + 1:]
+        if rec["count"] <= 10000:  # keep the record's text for the results-writer tests (CodeStatistics.h:22-37)
+            blocks = [b for b in open(path).read().replace("\r", "").split("Code: ") if b.strip()]
+            rec["text"] = "Code: " + blocks[rec["record_index"]].rstrip("\n") + "\n"
         kat[name] = rec
     json.dump(kat, open(os.path.join(HERE, "kat_results.json"), "w"), indent=1, sort_keys=True)
 
