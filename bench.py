@@ -127,7 +127,8 @@ class CpuReference:
             code.write_file(path)
             self.rc = Reference().code_from_file(path)
             self.kind = "reference"
-        self.cores = self.oracle.max_threads()
+        # all host cores this process may use (torchrun exports OMP_NUM_THREADS=1; the harnesses set the count themselves)
+        self.cores = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
 
     def patterns(self, first, n):
         return self.oc.depolarizing_bulk(SEED, first, n, P)

@@ -42,7 +42,7 @@ int fail(int code, const std::string& msg) {
 struct DevSide {
   int m = 0, dc = 0, dv = 0, E = 0, mw = 0;
   uint16_t* vrow = nullptr;  // [dv][n]
-  uint16_t* cvar = nullptr;  // [dc][m]
+  uint16_t* vchk = nullptr;  // [dv][n] check index of the k-th edge of variable v (CSC)
   BpLaunch cfg, user;        // resolved configuration / user overrides
   bool cfg_ok = false;
   std::string cfg_err;
@@ -70,6 +70,8 @@ struct qldpc_decoder {
   int lx_rows = 0, lz_rows = 0, lm_rows = 0;
   void* stage = nullptr;  // device staging for one-element-per-bit I/O
   size_t stage_bytes = 0;
+  cudaStream_t copy_stream = nullptr;  // H2D copies of host-supplied patterns overlap the decode of the previous slice
+  cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   uint32_t* pin = nullptr;  // pinned host staging for the weight-W generator
   size_t pin_words = 0;
   // measurement: launches per kernel class, and (when enabled) CUDA-event pairs on the launching stream
@@ -82,11 +84,16 @@ struct qldpc_decoder {
 
   ~qldpc_decoder() {
     cudaSetDevice(device);
-    for (int i = 0; i < 2; ++i) { cudaFree(s[i].vrow); cudaFree(s[i].cvar); }
+    for (int i = 0; i < 2; ++i) { cudaFree(s[i].vrow); cudaFree(s[i].vchk); }
     cudaFree(errX); cudaFree(errZ); cudaFree(synX); cudaFree(synZ); cudaFree(decX); cudaFree(decZ);
     cudaFree(sfX); cudaFree(sfZ); cudaFree(fflags); cudaFree(itX); cudaFree(itZ);
     cudaFree(counters); cudaFree(queues); cudaFree(lx); cudaFree(lz); cudaFree(lm); cudaFree(stage);
     if (pin) cudaFreeHost(pin);
+    for (int i = 0; i < 2; ++i) {
+      if (ev_ready[i]) cudaEventDestroy(ev_ready[i]);
+      if (ev_free[i]) cudaEventDestroy(ev_free[i]);
+    }
+    if (copy_stream) cudaStreamDestroy(copy_stream);
     for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : pool) cudaEventDestroy(e);
     if (own_stream) cudaStreamDestroy(own_stream);
@@ -240,8 +247,8 @@ int run_stats(qldpc_decoder* d, int nf, uint8_t* fflags) {
 
 int run_syndrome(qldpc_decoder* d, int nf) {
   Timed t(d, QLDPC_T_SYNDROME);
-  CU_TRY(launch_syndrome(d->errX, d->errZ, nf, d->n, d->nw, d->s[0].cvar, d->s[0].m, d->s[0].dc, d->s[0].mw, d->synX,
-                         d->s[1].cvar, d->s[1].m, d->s[1].dc, d->s[1].mw, d->synZ, d->stream));
+  CU_TRY(launch_syndrome(d->errX, d->errZ, nf, d->n, d->nw, d->s[0].vchk, d->s[0].dv, d->s[0].mw, d->synX, d->s[1].vchk,
+                         d->s[1].dv, d->s[1].mw, d->synZ, d->stream));
   return QLDPC_OK;
 }
 
@@ -471,19 +478,18 @@ int qldpc_decoder_create(const qldpc_code* code, int device_ordinal, int max_fra
       s.cfg_err = "code too large for the shared-memory-resident BP kernel";
       continue;
     }
-    std::vector<uint16_t> vrow((size_t)t.E), cvar((size_t)t.E);
+    std::vector<uint16_t> vrow((size_t)t.E), vchk((size_t)t.E);
     for (int v = 0; v < n; ++v)
       for (int k = 0; k < t.dv; ++k) {
         const int edge = t.var_edge[(size_t)v * t.dv + k];
         const int e = edge / t.dc, i = edge % t.dc;
         vrow[(size_t)k * n + v] = (uint16_t)(i * t.m + e);
+        vchk[(size_t)k * n + v] = (uint16_t)e;
       }
-    for (int e = 0; e < t.m; ++e)
-      for (int i = 0; i < t.dc; ++i) cvar[(size_t)i * t.m + e] = (uint16_t)t.chk_var[(size_t)e * t.dc + i];
     D_TRY(dev_alloc(s.vrow, vrow.size()));
-    D_TRY(dev_alloc(s.cvar, cvar.size()));
+    D_TRY(dev_alloc(s.vchk, vchk.size()));
     D_TRY(cudaMemcpy(s.vrow, vrow.data(), vrow.size() * 2, cudaMemcpyHostToDevice));
-    D_TRY(cudaMemcpy(s.cvar, cvar.data(), cvar.size() * 2, cudaMemcpyHostToDevice));
+    D_TRY(cudaMemcpy(s.vchk, vchk.data(), vchk.size() * 2, cudaMemcpyHostToDevice));
     resolve_config(d, side);  // failure is reported when the side is first used
   }
   const size_t F = (size_t)d->chunk;
@@ -702,6 +708,11 @@ int qldpc_get_statistics_weightw(qldpc_decoder* dec, int errorWeight, int64_t nu
   return read_counters(d, counters);
 }
 
+// Host-supplied error patterns are processed in slices of at most kPipeFrames frames: slice i+1 is copied to the device
+// on a second stream while slice i is packed, decoded and reduced (two staging buffers, events for hand-over), so
+// with pinned host memory the PCIe transfer hides behind the decode (or vice versa).
+static const int kPipeFrames = 1 << 17;
+
 static int stats_from_errors(qldpc_decoder* d, const void* xErrors, const void* zErrors, int elem, int64_t numErrors,
                              float errorProbability, int maxIterations, uint64_t* counters, uint8_t* perFrameFlags,
                              uint32_t* perFrameIters) {
@@ -710,20 +721,35 @@ static int stats_from_errors(qldpc_decoder* d, const void* xErrors, const void* 
   if (!xErrors || !zErrors) return fail(QLDPC_ERR_ARG, "null buffer");
   const int n = d->n;
   const size_t row = (size_t)n * elem;
-  rc = ensure_stage(d, 2 * row * std::min<int64_t>(d->chunk, std::max<int64_t>(numErrors, 1)));
+  const int64_t slice = std::min<int64_t>(std::min<int64_t>(d->chunk, kPipeFrames), std::max<int64_t>(numErrors, 1));
+  const size_t half = 2 * row * (size_t)slice;  // one staging buffer: x rows then z rows
+  rc = ensure_stage(d, 2 * half);
   if (rc) return rc;
+  if (!d->copy_stream) {
+    CU_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+    for (int i = 0; i < 2; ++i) {
+      CU_TRY(cudaEventCreateWithFlags(&d->ev_ready[i], cudaEventDisableTiming));
+      CU_TRY(cudaEventCreateWithFlags(&d->ev_free[i], cudaEventDisableTiming));
+    }
+  }
   CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
-  for (int64_t off = 0; off < numErrors; off += d->chunk) {
-    const int nf = (int)std::min<int64_t>(d->chunk, numErrors - off);
-    uint8_t* st0 = (uint8_t*)d->stage;
+  int i = 0;
+  for (int64_t off = 0; off < numErrors; off += slice, ++i) {
+    const int nf = (int)std::min<int64_t>(slice, numErrors - off);
+    const int b = i & 1;
+    uint8_t* st0 = (uint8_t*)d->stage + (size_t)b * half;
     uint8_t* st1 = st0 + row * nf;
-    CU_TRY(cudaMemcpyAsync(st0, (const uint8_t*)xErrors + off * row, row * nf, cudaMemcpyHostToDevice, d->stream));
-    CU_TRY(cudaMemcpyAsync(st1, (const uint8_t*)zErrors + off * row, row * nf, cudaMemcpyHostToDevice, d->stream));
+    if (i >= 2) CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_free[b], 0));
+    CU_TRY(cudaMemcpyAsync(st0, (const uint8_t*)xErrors + off * row, row * nf, cudaMemcpyHostToDevice, d->copy_stream));
+    CU_TRY(cudaMemcpyAsync(st1, (const uint8_t*)zErrors + off * row, row * nf, cudaMemcpyHostToDevice, d->copy_stream));
+    CU_TRY(cudaEventRecord(d->ev_ready[b], d->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_ready[b], 0));
     {
       Timed t(d, QLDPC_T_PACK, 2);
       CU_TRY(launch_pack(st0, elem, nf, n, d->nw, d->errX, d->stream));
       CU_TRY(launch_pack(st1, elem, nf, n, d->nw, d->errZ, d->stream));
     }
+    CU_TRY(cudaEventRecord(d->ev_free[b], d->stream));
     rc = run_syndrome(d, nf);
     if (rc) return rc;
     rc = finish_chunk(d, nf, off, errorProbability, maxIterations, perFrameFlags, perFrameIters);

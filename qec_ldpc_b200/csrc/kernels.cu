@@ -157,57 +157,53 @@ cudaError_t launch_generate(uint64_t seed, uint64_t first_frame, int nframes, in
 }
 
 // =====================================================================================================
-// Syndrome s = H e mod 2 (Quantum_LDPC_Code::GetSyndromeX/Z, Quantum_LDPC_Code.h:94-124): XOR of the dc error
-// bits of each check instead of the reference's dense row scan.  One warp per frame, error words staged in
-// shared memory, lanes over checks, ballot packs the result.
+// Syndrome s = H e mod 2 (Quantum_LDPC_Code::GetSyndromeX/Z, Quantum_LDPC_Code.h:94-124).  The reference scans the
+// dense row of every check; here the work is proportional to the error weight: one warp per frame walks the set
+// bits of the bit-packed error and flips the dv checks of each erroneous qubit in shared memory (vchk = CSC table).
 // =====================================================================================================
-__device__ __forceinline__ void syndrome_side(const uint32_t* __restrict__ ew, const uint16_t* __restrict__ cvar, int m,
-                                              int dc, int mw, uint32_t* __restrict__ out, int lane) {
-  for (int e0 = 0; e0 < m; e0 += 32) {
-    const int e = e0 + lane;
-    unsigned bit = 0;
-    if (e < m)
-      for (int i = 0; i < dc; ++i) {
-        const int v = cvar[i * m + e];
-        bit ^= (ew[v >> 5] >> (v & 31)) & 1u;
+__device__ __forceinline__ void syndrome_side(const uint32_t* __restrict__ err, int nw, const uint16_t* __restrict__ vchk,
+                                              int n, int dv, int mw, uint32_t* sm, uint32_t* __restrict__ out, int lane) {
+  for (int w = lane; w < mw; w += 32) sm[w] = 0u;
+  __syncwarp();
+  for (int w = lane; w < nw; w += 32) {
+    uint32_t word = err[w];
+    while (word) {
+      const int v = w * 32 + __ffs((int)word) - 1;
+      word &= word - 1u;
+      for (int k = 0; k < dv; ++k) {
+        const int e = vchk[k * n + v];
+        atomicXor(&sm[e >> 5], 1u << (e & 31));
       }
-    const unsigned w = __ballot_sync(0xffffffffu, bit);
-    if (lane == 0 && (e0 >> 5) < mw) out[e0 >> 5] = w;
+    }
   }
+  __syncwarp();
+  for (int w = lane; w < mw; w += 32) out[w] = sm[w];
+  __syncwarp();
 }
 
 __global__ void __launch_bounds__(256) syndrome_kernel(const uint32_t* __restrict__ errX, const uint32_t* __restrict__ errZ,
-                                                       int nframes, int n, int nw, const uint16_t* __restrict__ cvarX,
-                                                       int mX, int dcX, int mwX, uint32_t* __restrict__ synX,
-                                                       const uint16_t* __restrict__ cvarZ, int mZ, int dcZ, int mwZ,
+                                                       int nframes, int n, int nw, const uint16_t* __restrict__ vchkX,
+                                                       int dvX, int mwX, uint32_t* __restrict__ synX,
+                                                       const uint16_t* __restrict__ vchkZ, int dvZ, int mwZ,
                                                        uint32_t* __restrict__ synZ) {
   extern __shared__ uint32_t sh[];
   const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
-  uint32_t* ex = sh + (size_t)wib * 2 * nw;
-  uint32_t* ez = ex + nw;
+  uint32_t* sm = sh + (size_t)wib * max(mwX, mwZ);
   for (int f = warp; f < nframes; f += nwarps) {
-    for (int w = lane; w < nw; w += 32) {
-      ex[w] = errX[(size_t)f * nw + w];
-      ez[w] = errZ[(size_t)f * nw + w];
-    }
-    __syncwarp();
-    syndrome_side(ex, cvarX, mX, dcX, mwX, synX + (size_t)f * mwX, lane);
-    syndrome_side(ez, cvarZ, mZ, dcZ, mwZ, synZ + (size_t)f * mwZ, lane);
-    __syncwarp();
+    syndrome_side(errX + (size_t)f * nw, nw, vchkX, n, dvX, mwX, sm, synX + (size_t)f * mwX, lane);
+    syndrome_side(errZ + (size_t)f * nw, nw, vchkZ, n, dvZ, mwZ, sm, synZ + (size_t)f * mwZ, lane);
   }
-  (void)n;
 }
 
 cudaError_t launch_syndrome(const uint32_t* errX, const uint32_t* errZ, int nframes, int n, int nw,
-                            const uint16_t* cvarX, int mX, int dcX, int mwX, uint32_t* synX, const uint16_t* cvarZ,
-                            int mZ, int dcZ, int mwZ, uint32_t* synZ, cudaStream_t st) {
+                            const uint16_t* vchkX, int dvX, int mwX, uint32_t* synX, const uint16_t* vchkZ, int dvZ,
+                            int mwZ, uint32_t* synZ, cudaStream_t st) {
   if (nframes <= 0) return cudaSuccess;
   const int blocks = std::min((nframes + 7) / 8, 148 * 16);
-  const size_t sh = (size_t)8 * 2 * nw * sizeof(uint32_t);
-  syndrome_kernel<<<blocks, 256, sh, st>>>(errX, errZ, nframes, n, nw, cvarX, mX, dcX, mwX, synX, cvarZ, mZ, dcZ, mwZ,
-                                           synZ);
+  const size_t sh = (size_t)8 * std::max(mwX, mwZ) * sizeof(uint32_t);
+  syndrome_kernel<<<blocks, 256, sh, st>>>(errX, errZ, nframes, n, nw, vchkX, dvX, mwX, synX, vchkZ, dvZ, mwZ, synZ);
   return cudaGetLastError();
 }
 

@@ -26,10 +26,10 @@ cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, i
 // Philox depolarizing errors, bit-packed: errX, errZ [nframes][nw].
 cudaError_t launch_generate(uint64_t seed, uint64_t first_frame, int nframes, int n, int nw, Thresholds thr,
                             uint32_t* errX, uint32_t* errZ, cudaStream_t st);
-// s = H e (mod 2) for both sides from bit-packed errors; cvar tables [dc][m] per side.
+// s = H e (mod 2) for both sides from bit-packed errors; vchk = CSC tables [dv][n] (check index of the k-th edge).
 cudaError_t launch_syndrome(const uint32_t* errX, const uint32_t* errZ, int nframes, int n, int nw,
-                            const uint16_t* cvarX, int mX, int dcX, int mwX, uint32_t* synX,
-                            const uint16_t* cvarZ, int mZ, int dcZ, int mwZ, uint32_t* synZ, cudaStream_t st);
+                            const uint16_t* vchkX, int dvX, int mwX, uint32_t* synX, const uint16_t* vchkZ, int dvZ,
+                            int mwZ, uint32_t* synZ, cudaStream_t st);
 // rows of `bits` one-per-element (elem_size 1 or 4 bytes) <-> bit-packed words
 cudaError_t launch_pack(const void* src, int elem_size, int64_t rows, int cols, int words, uint32_t* dst, cudaStream_t st);
 cudaError_t launch_unpack(const uint32_t* src, int64_t rows, int cols, int words, uint8_t* dst, cudaStream_t st);
