@@ -14,7 +14,7 @@ namespace qldpc {
 // =====================================================================================================
 
 typedef void (*BpKernel)(const BpArgs);
-constexpr int kMaxT = 256;
+constexpr int kMaxT = 512;
 // one translation unit per shape (bp_shape_<dc>_<dv>.cu)
 #define QLDPC_SHAPES(X) X(6, 3) X(10, 4) X(10, 5) X(8, 4) X(8, 3) X(12, 6)
 #define QLDPC_DECL(DC, DV) BpKernel bp_shape_##DC##_##DV(int vec, int guard);
@@ -40,46 +40,58 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   cudaGetDevice(&dev);
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
-  int vec = cfg.vec;
-  if (vec == 0) {
-    for (int v : {4, 2, 1})
-      if ((int)bp_smem_bytes(v, E, m, n, mw, nw) <= smem_optin) { vec = v; break; }
-    if (vec == 0) { *why = kNoFit; return false; }
-  } else if (!(vec == 1 || vec == 2 || vec == 4) || (int)bp_smem_bytes(vec, E, m, n, mw, nw) > smem_optin) {
-    *why = kBadCfg;
-    return false;
+  // Candidate (tile width, warps per CTA) pairs are scored by the warps they keep resident per SM (shared memory and
+  // the register file both limit the CTA count; beyond ~20 warps the kernel is issue-bound and gains nothing) and by
+  // the warp-rounds wasted when the check phase (ceil(m/32) warp-tasks) and the variable phase (ceil(n/32)) do not
+  // divide evenly among the CTA's warps.  Wider tiles win ties (fewer shared-memory instructions per edge-update).
+  auto regs_of = [&](int v) {
+    int r = 0;
+    for (int guard : {0, 1, 3}) {
+      cudaFuncAttributes fa;
+      if (cudaFuncGetAttributes(&fa, lookup_kernel(dc, dv, v, guard)) == cudaSuccess) r = std::max(r, fa.numRegs);
+    }
+    cudaGetLastError();
+    return std::max(r, 32);
+  };
+  int vec = cfg.vec, threads = cfg.threads;
+  if (vec != 0 && !(vec == 1 || vec == 2 || vec == 4)) { *why = kBadCfg; return false; }
+  if (vec == 0 || threads == 0) {
+    const int wc = (m + 31) / 32, wv = (n + 31) / 32;
+    double best = -1.0;
+    int best_v = 0, best_w = 0;
+    for (int v : {4, 2, 1}) {
+      if (vec != 0 && v != vec) continue;
+      const int sm_bytes = (int)bp_smem_bytes(v, E, m, n, mw, nw);
+      if (sm_bytes > smem_optin) continue;
+      const int smem_ctas = std::max(1, smem_sm / (sm_bytes + 1024));
+      const int regs_v = (regs_of(v) + 7) / 8 * 8;
+      for (int w = 2; w <= kMaxT / 32; ++w) {
+        if (threads != 0 && 32 * w != threads) continue;
+        const int reg_ctas = 65536 / (regs_v * 32 * w);
+        if (reg_ctas < 1) continue;
+        const int resident = std::min(std::min(smem_ctas, reg_ctas), 32) * w;
+        const double waste = (double)((wc + w - 1) / w * w - wc) * dc + (double)((wv + w - 1) / w * w - wv) * dv * 2;
+        const double work = (double)wc * dc + (double)wv * dv * 2;
+        const double score = std::min(resident, 20) / 20.0 * (work / (work + waste)) + 0.004 * v + 0.0005 * std::min(resident, 32);
+        if (score > best) { best = score; best_v = v; best_w = w; }
+      }
+    }
+    if (best_v == 0) { *why = threads != 0 || vec != 0 ? kBadCfg : kNoFit; return false; }
+    vec = best_v;
+    threads = 32 * best_w;
   }
   const int smem = (int)bp_smem_bytes(vec, E, m, n, mw, nw);
-  int regs = 0;
+  if (smem > smem_optin) { *why = kBadCfg; return false; }
   for (int guard : {0, 1, 3}) {
-    BpKernel kg = lookup_kernel(dc, dv, vec, guard);
-    if (cudaFuncSetAttribute(kg, cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) {
+    if (cudaFuncSetAttribute(lookup_kernel(dc, dv, vec, guard), cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
+        cudaSuccess) {
       cudaGetLastError();
       *why = kNoFit;
       return false;
     }
-    cudaFuncAttributes fa;
-    cudaFuncGetAttributes(&fa, kg);
-    regs = std::max(regs, fa.numRegs);
   }
+  const int regs = regs_of(vec);
   BpKernel k = lookup_kernel(dc, dv, vec, 3);
-  int threads = cfg.threads;
-  if (threads == 0) {
-    // Each phase hands one node to a thread; pick the warp count that wastes the fewest warp-rounds over the
-    // check phase (ceil(m/32) warp-tasks) and the variable phase (ceil(n/32)), preferring 4-5 warps so that
-    // several CTAs share an SM and hide each other's barriers.
-    const int wc = (m + 31) / 32, wv = (n + 31) / 32;
-    const int smem_ctas = std::max(1, smem_sm / (smem + 1024));
-    double best = 1e30;
-    for (int w = 2; w <= kMaxT / 32; ++w) {
-      const double waste = (double)((wc + w - 1) / w * w - wc) * dc + (double)((wv + w - 1) / w * w - wv) * dv * 2;
-      const double work = (double)wc * dc + (double)wv * dv * 2;
-      const int resident = std::min(smem_ctas, std::max(1, 768 / (32 * w))) * w;  // warps per SM
-      const double occ_pen = resident >= 16 ? 0.0 : (16 - resident) * 0.03;
-      const double score = waste / work + occ_pen + 0.002 * std::abs(w - 5);
-      if (score < best) { best = score; threads = 32 * w; }
-    }
-  }
   if (threads % 32 || threads < 32 || threads > kMaxT) { *why = kBadCfg; return false; }
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem) != cudaSuccess || occ < 1) {

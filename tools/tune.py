@@ -1,10 +1,12 @@
-"""Launch-shape sweep for the BP tile kernel on J4K5L10P61 (p=0.05, 50 iterations): tile width x threads per CTA."""
+"""Launch-shape sweep for the BP tile kernel (p=0.05, 50 iterations): tile width x threads per CTA.
+Usage: python tools/tune.py [frames] [J,K,L,P,sigma,tau]"""
 import sys
 sys.path.insert(0, ".")
 import qec_ldpc_b200 as q
 
 n = int(sys.argv[1]) if len(sys.argv) > 1 else 400_000
-code = q.Code.qc(4, 5, 10, 61, 9, 49)
+prm = [int(v) for v in sys.argv[2].split(",")] if len(sys.argv) > 2 else [4, 5, 10, 61, 9, 49]
+code = q.Code.qc(*prm)
 dec = q.Decoder(code, 0, n)
 dec.enable_timing(True)
 best = {}
