@@ -260,6 +260,27 @@ def run_native(args):
     chk = dec.get_statistics_depolarizing(SEED, first_frame(0), F, P, MAXIT)["counters"]
     assert np.array_equal(chk, e2e_counters), "host-buffer path and device-generated path disagree"
 
+    # two more end-to-end views, reported next to the primary one: (a) the same call with one BYTE per qubit
+    # (qldpc_get_stats_from_errors_u8: a quarter of the PCIe traffic), (b) the Monte-Carlo call itself,
+    # qldpc_get_statistics_depolarizing (what GetStatistics(W, COUNT, p, MAXIT) is in the reference's driver,
+    # main.cu:101): scalars in, counters out, errors generated on the device -- timed on the host clock.
+    xb, zb = xh.to(torch.uint8).pin_memory(), zh.to(torch.uint8).pin_memory()
+    dec.get_stats_from_errors_ptr(xb.data_ptr(), zb.data_ptr(), F, P, MAXIT, elem=1)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        u8_counters = dec.get_stats_from_errors_ptr(xb.data_ptr(), zb.data_ptr(), F, P, MAXIT, elem=1)
+    torch.cuda.synchronize()
+    e2e_u8_s = allreduce_max(time.perf_counter() - t0, "cuda")
+    assert np.array_equal(chk, u8_counters)
+    barrier()
+    t0 = time.perf_counter()
+    for s in range(args.steps):
+        dec.get_statistics_depolarizing(SEED, first_frame(s), F, P, MAXIT)
+    torch.cuda.synchronize()
+    e2e_gs_s = allreduce_max(time.perf_counter() - t0, "cuda")
+    del xb, zb
+
     if rank == 0:
         frames = int(gc[0])
         eu = int(gc[9]) * code.EX + int(gc[10]) * code.EZ
@@ -306,7 +327,12 @@ def run_native(args):
             "e2e": {"value": F * n_gpus * args.steps / e2e_s, "unit": "frames/s",
                     "h2d_bytes_per_step": 2 * F * n * 4, "d2h_bytes_per_step": q.NUM_COUNTERS * 8,
                     "api": "qldpc_get_stats_from_errors_i32 (DecoderGPU::GetStats layout, pinned host int32)",
-                    "ms_per_step": 1e3 * e2e_s / args.steps},
+                    "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "u8_patterns": {"value": F * n_gpus * args.steps / e2e_u8_s, "unit": "frames/s",
+                                    "h2d_bytes_per_step": 2 * F * n, "api": "qldpc_get_stats_from_errors_u8"},
+                    "device_generated": {"value": F * n_gpus * args.steps / e2e_gs_s, "unit": "frames/s",
+                                         "h2d_bytes_per_step": 0, "d2h_bytes_per_step": q.NUM_COUNTERS * 8,
+                                         "api": "qldpc_get_statistics_depolarizing (host wall clock)"}},
             "gpu_launches": int(sum(klaunch.values())),
             "clocks": clocks,
         }
