@@ -115,9 +115,12 @@ int qldpc_decoder_create(const qldpc_code* code, int device_ordinal, int max_fra
 void qldpc_decoder_destroy(qldpc_decoder* dec);
 /* Run all work of this handle on the given cudaStream_t (NULL = the handle's own stream). */
 int qldpc_decoder_set_stream(qldpc_decoder* dec, void* cuda_stream);
-/* Tuning knobs (0 = heuristic): frames per CTA tile (1, 2 or 4) and threads per CTA for side 0/1. */
+/* Tuning knobs (0 = heuristic): frames per CTA tile (1, 2 or 4) and threads per CTA for side 0/1.
+ * frames_per_tile = -1 selects the global-memory (HBM-resident) BP path, which is otherwise used only for shapes the
+ * shared-memory tile kernel does not cover (no instantiation for the degrees, or a frame larger than shared memory). */
 int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, int threads_per_cta, int ctas_per_sm);
-/* Launch geometry in use: out[0..5] = vec, threads, ctas_per_sm, grid, dyn_smem_bytes, regs for `side`. */
+/* Launch geometry in use: out[0..7] = vec (-1: global-memory path), threads, ctas_per_sm, grid, dyn_smem_bytes, regs,
+ * SM count, frames per launch. */
 int qldpc_decoder_launch_info(qldpc_decoder* dec, int side, int32_t out[8]);
 
 /* Decoder::Decode / DecoderCPU::Decode on a batch of frames (Decoder.h:40-43, DecoderCPU.h:317-390;

@@ -14,7 +14,7 @@ CLI = os.path.join(LIBDIR, "qec_ldpc")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
-LIB_SOURCES = ["code.cpp", "kernels.cu", "decoder.cu"] + sorted(
+LIB_SOURCES = ["code.cpp", "kernels.cu", "decoder.cu", "bp_global.cu"] + sorted(
     f for f in os.listdir(CSRC) if f.startswith("bp_shape_") and f.endswith(".cu"))
 
 
@@ -53,7 +53,7 @@ def build_library(force=False, verbose=False):
         for cmd, p in procs:
             if p.wait() != 0:
                 raise RuntimeError("nvcc failed: " + " ".join(cmd))
-        cmd = [_nvcc(), "-shared", "-o", LIB] + objs
+        cmd = [_nvcc(), "-shared", "-gencode", "arch=compute_100a,code=sm_100a", "-o", LIB] + objs
         subprocess.run(cmd, check=True, env=_env())
     return LIB
 

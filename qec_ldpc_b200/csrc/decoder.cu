@@ -46,6 +46,15 @@ struct DevSide {
   BpLaunch cfg, user;        // resolved configuration / user overrides
   bool cfg_ok = false;
   std::string cfg_err;
+  // global-memory fallback path (bp_global.cu): shapes without a tile-kernel instantiation, frames too large for
+  // shared memory, or forced with frames_per_tile = -1
+  bool use_global = false, force_global = false;
+  uint32_t* gvrow = nullptr;  // [dv][n] row i*m+e
+  uint32_t* gcvar = nullptr;  // [dc][m] variable of the i-th edge of check e
+  float* gmsg = nullptr;
+  uint8_t* gbytes = nullptr;
+  uint32_t* gwords = nullptr;
+  int gbatch = 0;
 };
 
 template <typename T>
@@ -84,7 +93,10 @@ struct qldpc_decoder {
 
   ~qldpc_decoder() {
     cudaSetDevice(device);
-    for (int i = 0; i < 2; ++i) { cudaFree(s[i].vrow); cudaFree(s[i].vchk); }
+    for (int i = 0; i < 2; ++i) {
+      cudaFree(s[i].vrow); cudaFree(s[i].vchk); cudaFree(s[i].gvrow); cudaFree(s[i].gcvar);
+      cudaFree(s[i].gmsg); cudaFree(s[i].gbytes); cudaFree(s[i].gwords);
+    }
     cudaFree(errX); cudaFree(errZ); cudaFree(synX); cudaFree(synZ); cudaFree(decX); cudaFree(decZ);
     cudaFree(sfX); cudaFree(sfZ); cudaFree(fflags); cudaFree(itX); cudaFree(itZ);
     cudaFree(counters); cudaFree(queues); cudaFree(lx); cudaFree(lz); cudaFree(lm); cudaFree(stage);
@@ -174,14 +186,61 @@ int upload_logical(const BitMatrix& L, int r0, int rows, int c0_word_of, int wor
   return QLDPC_OK;
 }
 
+// Device tables and work buffers of the global-memory path, built on first need.
+int ensure_global(qldpc_decoder* d, int side) {
+  DevSide& s = d->s[side];
+  if (s.gmsg) return QLDPC_OK;
+  const SideTables& t = d->code.side[side];
+  const int n = d->n;
+  if (std::max(s.dc, s.dv) > 32) return fail(QLDPC_ERR_UNSUPPORTED, "node degree above 32");
+  std::vector<uint32_t> vrow((size_t)t.E), cvar((size_t)t.E);
+  for (int v = 0; v < n; ++v)
+    for (int k = 0; k < t.dv; ++k) {
+      const int edge = t.var_edge[(size_t)v * t.dv + k];
+      vrow[(size_t)k * n + v] = (uint32_t)((edge % t.dc) * t.m + edge / t.dc);
+    }
+  for (int e = 0; e < t.m; ++e)
+    for (int i = 0; i < t.dc; ++i) cvar[(size_t)i * t.m + e] = (uint32_t)t.chk_var[(size_t)e * t.dc + i];
+  // batch: as many frames as fit in ~2 GB of messages, a multiple of 32, at most the decoder's chunk
+  long long batch = (long long)(2.0e9 / ((double)t.E * 4.0)) / 32 * 32;
+  batch = std::max<long long>(32, std::min<long long>(batch, ((long long)d->chunk + 31) / 32 * 32));
+  s.gbatch = (int)std::min<long long>(batch, 1 << 16);
+  size_t mb, bb, wb;
+  global_bp_bytes(s.m, s.dc, s.gbatch, &mb, &bb, &wb);
+  CU_TRY(dev_alloc(s.gvrow, vrow.size()));
+  CU_TRY(dev_alloc(s.gcvar, cvar.size()));
+  CU_TRY(cudaMemcpy(s.gvrow, vrow.data(), vrow.size() * 4, cudaMemcpyHostToDevice));
+  CU_TRY(cudaMemcpy(s.gcvar, cvar.data(), cvar.size() * 4, cudaMemcpyHostToDevice));
+  CU_TRY(cudaMalloc((void**)&s.gbytes, bb));
+  CU_TRY(cudaMalloc((void**)&s.gwords, wb));
+  CU_TRY(cudaMalloc((void**)&s.gmsg, mb));
+  return QLDPC_OK;
+}
+
 int resolve_config(qldpc_decoder* d, int side) {
   DevSide& s = d->s[side];
   BpLaunch cfg = s.user;
   const char* why = "";
-  s.cfg_ok = bp_configure(s.dc, s.dv, s.m, d->n, d->num_sms, cfg, &why);
+  s.use_global = false;
+  s.cfg_ok = !s.force_global && s.E < 65536 && bp_configure(s.dc, s.dv, s.m, d->n, d->num_sms, cfg, &why);
   if (!s.cfg_ok) {
-    s.cfg_err = why;
-    return fail(QLDPC_ERR_UNSUPPORTED, s.cfg_err);
+    // no tile kernel for this side: the HBM-resident path takes over (still on the GPU; slower, see bp_global.cu)
+    if (s.m > 65535) {
+      s.cfg_err = "more than 65535 checks per side";
+      return fail(QLDPC_ERR_UNSUPPORTED, s.cfg_err);
+    }
+    int rc = ensure_global(d, side);
+    if (rc) {
+      s.cfg_err = qldpc_last_error();
+      return rc;
+    }
+    s.use_global = true;
+    s.cfg_ok = true;
+    s.cfg = BpLaunch();
+    s.cfg.vec = -1;
+    s.cfg.threads = 128;
+    s.cfg.grid = s.gbatch;
+    return QLDPC_OK;
   }
   s.cfg = cfg;
   return QLDPC_OK;
@@ -226,6 +285,15 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
     a.prior = prior;
     a.trace_q = trace_q; a.trace_r = trace_r; a.trace_cap = trace_cap;
     Timed t(d, side ? QLDPC_T_BP_Z : QLDPC_T_BP_X);
+    if (s.use_global) {
+      if (trace_q || trace_r) return fail(QLDPC_ERR_UNSUPPORTED, "message taps are not available on the global-memory path");
+      GlobalBpArgs g;
+      g.m = s.m; g.n = d->n; g.dc = s.dc; g.dv = s.dv; g.mw = s.mw; g.nw = d->nw;
+      g.maxit = maxIterations; g.batch = s.gbatch; g.prior = prior;
+      g.vrow = s.gvrow; g.cvar = s.gcvar; g.msg = s.gmsg; g.bytes = s.gbytes; g.words = s.gwords;
+      CU_TRY(global_bp_run(g, a.syn, a.dec, a.flags, a.iters, nf, nullptr, d->stream));
+      continue;
+    }
     CU_TRY(bp_launch(s.dc, s.dv, s.cfg, a, nf, division_guard(prior, s.dv), d->stream));
   }
   return QLDPC_OK;
@@ -473,9 +541,9 @@ int qldpc_decoder_create(const qldpc_code* code, int device_ordinal, int max_fra
     const SideTables& t = d->code.side[side];
     DevSide& s = d->s[side];
     s.m = t.m; s.dc = t.dc; s.dv = t.dv; s.E = t.E; s.mw = (t.m + 31) / 32;
-    if (t.E >= 65536) {
+    if (t.m > 65535) {
       s.cfg_ok = false;
-      s.cfg_err = "code too large for the shared-memory-resident BP kernel";
+      s.cfg_err = "more than 65535 checks per side";
       continue;
     }
     std::vector<uint16_t> vrow((size_t)t.E), vchk((size_t)t.E);
@@ -529,6 +597,9 @@ int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, i
   if (!dec || side < 0 || side > 1) return fail(QLDPC_ERR_ARG, "bad argument");
   CU_TRY(cudaSetDevice(dec->device));
   BpLaunch keep = dec->s[side].user;
+  const bool keep_force = dec->s[side].force_global;
+  dec->s[side].force_global = frames_per_tile < 0;
+  if (frames_per_tile < 0) frames_per_tile = 0;
   dec->s[side].user = BpLaunch();
   dec->s[side].user.vec = frames_per_tile;
   dec->s[side].user.threads = threads_per_cta;
@@ -536,6 +607,7 @@ int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, i
   int rc = resolve_config(dec, side);
   if (rc) {
     dec->s[side].user = keep;
+    dec->s[side].force_global = keep_force;
     resolve_config(dec, side);
     return fail(rc, "configuration rejected");
   }

@@ -23,6 +23,20 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
 // guard: division range tests compiled in (0 none, 1 numerator, 3 both), see bp_kernel.cuh:div_fast
 cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, int guard, cudaStream_t st);
 
+// Global-memory fallback path (bp_global.cu).
+struct GlobalBpArgs {
+  int m, n, dc, dv, mw, nw, maxit, batch;
+  float prior;
+  const uint32_t* vrow;  // [dv][n]
+  const uint32_t* cvar;  // [dc][m]
+  float* msg;            // [E][batch]
+  uint8_t* bytes;        // syndrome bytes [m][batch] + 5 per-frame byte arrays
+  uint32_t* words;       // iteration counts [batch] + a counter
+};
+size_t global_bp_bytes(int m, int dc, int batch, size_t* msg_bytes, size_t* byte_bytes, size_t* word_bytes);
+cudaError_t global_bp_run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8_t* flags, uint32_t* iters,
+                          int nframes, int* launches, cudaStream_t st);
+
 // Philox depolarizing errors, bit-packed: errX, errZ [nframes][nw].
 cudaError_t launch_generate(uint64_t seed, uint64_t first_frame, int nframes, int n, int nw, Thresholds thr,
                             uint32_t* errX, uint32_t* errZ, cudaStream_t st);

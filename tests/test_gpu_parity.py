@@ -279,3 +279,37 @@ def test_division_fast_path_is_correctly_rounded(decoders):
     r = dec.debug_division_check(20261018, 1 << 28)
     assert r["mismatches"] == 0
     assert r["zero_numerators"] > (1 << 28) // 20 and 0 < r["deferred"] < (1 << 28) // 2
+
+
+@pytest.mark.parametrize("code,nf", [("C1", 3000), ("C2", 700)])
+def test_global_memory_path_matches_oracle(qldpc, oracle, code, nf):
+    """The HBM-resident fallback path (bp_global.cu), forced on codes the tile kernel also covers: identical counters,
+    flags and iteration counts."""
+    gc = qldpc.Code.qc(*CODES[code])
+    dec = qldpc.Decoder(gc, 0, 512)  # several batches and chunks
+    for side in (0, 1):
+        dec.configure(side, -1, 0, 0)
+        assert dec.launch_info(side)["vec"] == -1
+    oc = ocode(oracle, code, gc)
+    p, maxit = CFG[code]
+    a = dec.get_statistics_depolarizing(77, 3, nf, p, maxit, per_frame=True)
+    b = oc.run_depolarizing(77, 3, nf, p, maxit)
+    assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
+    assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))
+    for side in (0, 1):
+        dec.configure(side, 0, 0, 0)
+    assert np.array_equal(dec.get_statistics_depolarizing(77, 3, nf, p, maxit)["counters"], b["counters"])
+
+
+@pytest.mark.parametrize("prm,maxit", [((2, 2, 4, 11, 10, 2), 25), ((3, 4, 14, 13, 3, 2), 31)])
+def test_shapes_without_tile_kernel_use_global_path(qldpc, oracle, prm, maxit):
+    """(check degree, variable degree) pairs with no compiled tile kernel decode through the global-memory path."""
+    gc = qldpc.Code.qc(*prm)
+    dec = qldpc.Decoder(gc, 0, 4096)
+    assert dec.launch_info(0)["vec"] == -1
+    oc = oracle.code_qc(*prm)
+    oc.set_logical(gc.dense_matrix(2))
+    a = dec.get_statistics_depolarizing(5, 0, 2500, 0.04, maxit, per_frame=True)
+    b = oc.run_depolarizing(5, 0, 2500, 0.04, maxit)
+    assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
+    assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))
