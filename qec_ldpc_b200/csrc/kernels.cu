@@ -41,7 +41,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   cudaDeviceGetAttribute(&smem_optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
   cudaDeviceGetAttribute(&smem_sm, cudaDevAttrMaxSharedMemoryPerMultiprocessor, dev);
   // Candidate (tile width, warps per CTA) pairs are scored by the warps they keep resident per SM (shared memory and
-  // the register file both limit the CTA count; beyond ~20 warps the kernel is issue-bound and gains nothing) and by
+  // the register file both limit the CTA count; beyond ~16 warps the kernel gains nothing) and by
   // the warp-rounds wasted when the check phase (ceil(m/32) warp-tasks) and the variable phase (ceil(n/32)) do not
   // divide evenly among the CTA's warps.  Wider tiles win ties (fewer shared-memory instructions per edge-update).
   auto regs_of = [&](int v) {
@@ -72,7 +72,12 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
         const int resident = std::min(std::min(smem_ctas, reg_ctas), 32) * w;
         const double waste = (double)((wc + w - 1) / w * w - wc) * dc + (double)((wv + w - 1) / w * w - wv) * dv * 2;
         const double work = (double)wc * dc + (double)wv * dv * 2;
-        const double score = std::min(resident, 20) / 20.0 * (work / (work + waste)) + 0.004 * v + 0.0005 * std::min(resident, 32);
+        // A CTA whose warp count is not a multiple of 4 loads one SM sub-partition with two of its warps; since the
+        // packed-FP32 kernel keeps the FMA pipe ~2/3 busy, that sub-partition then paces every phase of the CTA
+        // (measured on the Z side of J4K5L10P61: 4 warps 9.85e11 vs 5 warps 9.33e11 edge-updates/s).
+        const double balance = w % 4 == 0 ? 1.0 : 0.92;
+        const double score = std::min(resident, 16) / 16.0 * (work / (work + waste)) * balance + 0.004 * v +
+                             0.0005 * std::min(resident, 32);
         if (score > best) { best = score; best_v = v; best_w = w; }
       }
     }
