@@ -21,7 +21,7 @@ __global__ void check(unsigned long long* out) {
     float x0 = prob(s) * prob(s), x1 = prob(s) * prob(s), y0 = x0 + prob(s), y1 = x1 + prob(s);
     bool u = false;
     float q0 = div_fast<0>(x0, y0, u), q1 = div_fast<0>(x1, y1, u);
-    Pack<2> q = div_fast_pack<0, 2>(Pack<2>{make_float2(x0, x1)}, Pack<2>{make_float2(y0, y1)}, u);
+    Pack<2> q = div_fast_pack<0, 2>(Pack<2>{make_float2(x0, x1)}, Pack<2>{make_float2(-y0, -y1)}, u);
     auto same = [](float a, float b) { return (a != a && b != b) || __float_as_uint(a) == __float_as_uint(b); };
     bad_div += !same(q.get(0), q0) + !same(q.get(1), q1);
     Pack<2> om = pfma(Pack<2>{make_float2(x0, x1)}, Pack<2>::splat(-1.0f), Pack<2>::splat(1.0f));
