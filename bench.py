@@ -301,7 +301,12 @@ def run_native(args):
         if os.path.exists(tpath):
             traffic = json.load(open(tpath)).get("dram_bytes_per_launch")
         sm_mhz = clocks["sm_mhz"] or 1965.0
-        smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9  # GB/s at the SM clock sampled under load
+        smem_nominal = 148 * 128 * sm_mhz * 1e6 / 1e9  # GB/s at the SM clock sampled under load
+        smem_peak, smem_src = smem_nominal, "nominal 148 SM x 128 B/clk x %.0f MHz (sampled under load)" % sm_mhz
+        spath = os.path.join(ROOT, "profiles", "smem_peak.json")
+        if os.path.exists(spath):  # measured by tools/micro/smem_bw.cu (LDS.128 + STS.128, the kernel's 1:1 mix)
+            smem_peak = float(json.load(open(spath))["roofline_denominator_gbs"])
+            smem_src = "measured (profiles/smem_peak.json, tools/micro/smem_bw.cu); nominal %.0f GB/s" % smem_nominal
         step_kernel_ms = sum(kms.values())
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": n_gpus, "steps": args.steps,
@@ -321,7 +326,7 @@ def run_native(args):
                                  "see smem_roofline for the tier that actually holds the state"},
             "smem_roofline": {"bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
                               "frac": achieved / smem_peak,
-                              "peak_source": "nominal 148 SM x 128 B/clk x %.0f MHz (sampled under load)" % sm_mhz},
+                              "peak_source": smem_src},
             "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
             "launch": {"x": info[0], "z": info[1]},
             "e2e": {"value": F * n_gpus * args.steps / e2e_s, "unit": "frames/s",

@@ -160,9 +160,8 @@ int ensure_stage(qldpc_decoder* d, size_t bytes) {
   return QLDPC_OK;
 }
 
-// logical rows [r0, r0+rows) restricted to bit-columns [c0, c0 + 32*words) -> transposed, row-padded LT[w][rows_pad]
-int upload_logical(const BitMatrix& L, int r0, int rows, int c0_word_of, int words, int n, bool z_part, uint32_t*& dst) {
-  (void)c0_word_of;
+// logical rows [r0, r0+rows): x-part words then z-part words (or the z-part alone), transposed and row-padded LT[w][rows_pad]
+int upload_logical(const BitMatrix& L, int r0, int rows, int words, int n, bool z_part, uint32_t*& dst) {
   dst = nullptr;
   if (rows == 0) return QLDPC_OK;
   const int rows_pad = (rows + 31) & ~31;
@@ -576,9 +575,9 @@ int qldpc_decoder_create(const qldpc_code* code, int device_ordinal, int max_fra
   D_TRY(dev_alloc(d->queues, (size_t)2));
   const Code& c = d->code;
   d->lx_rows = c.lx; d->lz_rows = c.lz; d->lm_rows = c.lm;
-  int rc = upload_logical(c.logical, 0, c.lx, 0, d->nw, n, false, d->lx);
-  if (!rc) rc = upload_logical(c.logical, c.lx, c.lz, 0, d->nw, n, true, d->lz);
-  if (!rc) rc = upload_logical(c.logical, c.lx + c.lz, c.lm, 0, 2 * d->nw, n, false, d->lm);
+  int rc = upload_logical(c.logical, 0, c.lx, d->nw, n, false, d->lx);
+  if (!rc) rc = upload_logical(c.logical, c.lx, c.lz, d->nw, n, true, d->lz);
+  if (!rc) rc = upload_logical(c.logical, c.lx + c.lz, c.lm, 2 * d->nw, n, false, d->lm);
   if (rc) return bail(rc);
 #undef D_TRY
   *out = d;
