@@ -76,8 +76,11 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
         // packed-FP32 kernel keeps the FMA pipe ~2/3 busy, that sub-partition then paces every phase of the CTA
         // (measured on the Z side of J4K5L10P61: 4 warps 9.85e11 vs 5 warps 9.33e11 edge-updates/s).
         const double balance = w % 4 == 0 ? 1.0 : 0.92;
-        const double score = std::min(resident, 16) / 16.0 * (work / (work + waste)) * balance + 0.004 * v +
-                             0.0005 * std::min(resident, 32);
+        // beyond 16 warps extra residency still buys a few per cent (measured: 28 warps of the 2-slot tile beat 20 warps
+        // of the 4-slot tile by 2-4%), which outweighs the wider tile's saving in shared-memory instructions
+        // (tiles of 2 or 4 slots use the packed fp32x2 arithmetic, the 1-slot tile cannot)
+        const double score = std::min(resident, 16) / 16.0 * (work / (work + waste)) * balance + 0.001 * v +
+                             (v >= 2 ? 0.01 : 0.0) + 0.001 * std::min(resident, 32);
         if (score > best) { best = score; best_v = v; best_w = w; }
       }
     }
