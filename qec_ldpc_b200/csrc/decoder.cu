@@ -604,6 +604,8 @@ int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, i
   dec->s[side].user.threads = threads_per_cta;
   dec->s[side].user.ctas_per_sm = ctas_per_sm;
   int rc = resolve_config(dec, side);
+  if (!rc && !dec->s[side].force_global && dec->s[side].use_global && (frames_per_tile > 0 || threads_per_cta > 0))
+    rc = QLDPC_ERR_ARG;  // an explicit tile shape that does not fit must not silently become the fallback path
   if (rc) {
     dec->s[side].user = keep;
     dec->s[side].force_global = keep_force;

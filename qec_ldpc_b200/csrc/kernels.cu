@@ -80,7 +80,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
         // of the 4-slot tile by 2-4%), which outweighs the wider tile's saving in shared-memory instructions
         // (tiles of 2 or 4 slots use the packed fp32x2 arithmetic, the 1-slot tile cannot)
         const double score = std::min(resident, 16) / 16.0 * (work / (work + waste)) * balance + 0.001 * v +
-                             (v >= 2 ? 0.01 : 0.0) + 0.001 * std::min(resident, 32);
+                             (v >= 2 ? 0.02 : 0.0) + 0.001 * std::min(resident, 32);
         if (score > best) { best = score; best_v = v; best_w = w; }
       }
     }
