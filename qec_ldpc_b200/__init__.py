@@ -238,6 +238,12 @@ class Decoder:
         _check(self._lib.qldpc_decode_batch(self.h, _ptr(sx), _ptr(sz), nf, p, maxit, _ptr(ox), _ptr(oz), _ptr(fl), _ptr(it)))
         return ox, oz, fl, it
 
+    def decode_batch_ptr(self, synX_ptr, synZ_ptr, nframes, p, maxit, outX_ptr, outZ_ptr, flags_ptr, iters_ptr=0):
+        """Host pointers (e.g. pinned torch tensors): bytes in, bytes out, as qldpc_decode_batch documents."""
+        _check(self._lib.qldpc_decode_batch(self.h, C.c_void_p(synX_ptr), C.c_void_p(synZ_ptr), nframes, p, maxit,
+                                            C.c_void_p(outX_ptr), C.c_void_p(outZ_ptr), C.c_void_p(flags_ptr),
+                                            C.c_void_p(iters_ptr) if iters_ptr else None))
+
     def decode_batch_device(self, d_synX, d_synZ, nframes, p, maxit, d_outX, d_outZ, d_flags, d_iters=0):
         _check(self._lib.qldpc_decode_batch_device(self.h, C.c_void_p(d_synX), C.c_void_p(d_synZ), nframes, p, maxit,
                                                 C.c_void_p(d_outX), C.c_void_p(d_outZ), C.c_void_p(d_flags),

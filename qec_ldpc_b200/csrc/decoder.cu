@@ -79,8 +79,10 @@ struct qldpc_decoder {
   int lx_rows = 0, lz_rows = 0, lm_rows = 0;
   void* stage = nullptr;  // device staging for one-element-per-bit I/O
   size_t stage_bytes = 0;
-  cudaStream_t copy_stream = nullptr;  // H2D copies of host-supplied patterns overlap the decode of the previous slice
+  // host-buffer entry points run as a pipeline: H2D of the next slice and D2H of the previous one overlap the decode
+  cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
+  cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
   uint32_t* pin = nullptr;  // pinned host staging for the weight-W generator
   size_t pin_words = 0;
   // measurement: launches per kernel class, and (when enabled) CUDA-event pairs on the launching stream
@@ -104,8 +106,11 @@ struct qldpc_decoder {
     for (int i = 0; i < 2; ++i) {
       if (ev_ready[i]) cudaEventDestroy(ev_ready[i]);
       if (ev_free[i]) cudaEventDestroy(ev_free[i]);
+      if (ev_done[i]) cudaEventDestroy(ev_done[i]);
+      if (ev_out_free[i]) cudaEventDestroy(ev_out_free[i]);
     }
     if (copy_stream) cudaStreamDestroy(copy_stream);
+    if (d2h_stream) cudaStreamDestroy(d2h_stream);
     for (auto& p : pending) { cudaEventDestroy(p.a); cudaEventDestroy(p.b); }
     for (auto e : pool) cudaEventDestroy(e);
     if (own_stream) cudaStreamDestroy(own_stream);
@@ -148,6 +153,22 @@ void drain_timing(qldpc_decoder* d) {
   }
   d->pending.clear();
   cudaGetLastError();
+}
+
+// Slice size of the host-buffer pipelines (frames).
+const int kPipeFrames = 1 << 17;
+
+int ensure_pipeline(qldpc_decoder* d) {
+  if (d->copy_stream) return QLDPC_OK;
+  CU_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
+  CU_TRY(cudaStreamCreateWithFlags(&d->d2h_stream, cudaStreamNonBlocking));
+  for (int i = 0; i < 2; ++i) {
+    CU_TRY(cudaEventCreateWithFlags(&d->ev_ready[i], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&d->ev_free[i], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&d->ev_done[i], cudaEventDisableTiming));
+    CU_TRY(cudaEventCreateWithFlags(&d->ev_out_free[i], cudaEventDisableTiming));
+  }
+  return QLDPC_OK;
 }
 
 int ensure_stage(qldpc_decoder* d, size_t bytes) {
@@ -673,39 +694,67 @@ int qldpc_decode_batch(qldpc_decoder* dec, const uint8_t* synX, const uint8_t* s
   int rc = check_common(dec, nframes, maxIterations);
   if (rc) return rc;
   if (!synX || !synZ || !outX || !outZ || !outFlags) return fail(QLDPC_ERR_ARG, "null buffer");
+  // Three-stage pipeline over slices of at most kPipeFrames frames, two staging buffers per direction:
+  //   copy stream : H2D of slice i+1          (waits until slice i-1 has been packed out of that buffer)
+  //   main stream : pack, BP X/Z, unpack, flags of slice i   (waits until slice i-2 has left the output buffer)
+  //   d2h stream  : D2H of slice i-1
   qldpc_decoder* d = dec;
   const int n = d->n, mX = d->s[0].m, mZ = d->s[1].m;
-  const size_t per = (size_t)std::max(n, std::max(mX, mZ));
-  rc = ensure_stage(d, 2 * per * std::min<int64_t>(d->chunk, std::max<int64_t>(nframes, 1)));
+  const int64_t slice = std::min<int64_t>(std::min<int64_t>(d->chunk, kPipeFrames), std::max<int64_t>(nframes, 1));
+  const size_t in_bytes = (size_t)(mX + mZ) * slice;
+  const size_t out_bytes = ((size_t)2 * n + 1) * slice + 15;
+  const size_t it_bytes = (size_t)8 * slice;
+  const size_t one = (in_bytes + out_bytes + it_bytes + 63) / 16 * 16;
+  rc = ensure_stage(d, 2 * one);
   if (rc) return rc;
-  for (int64_t off = 0; off < nframes; off += d->chunk) {
-    const int nf = (int)std::min<int64_t>(d->chunk, nframes - off);
-    uint8_t* st0 = (uint8_t*)d->stage;
-    uint8_t* st1 = st0 + per * nf;
-    CU_TRY(cudaMemcpyAsync(st0, synX + off * mX, (size_t)nf * mX, cudaMemcpyHostToDevice, d->stream));
-    CU_TRY(cudaMemcpyAsync(st1, synZ + off * mZ, (size_t)nf * mZ, cudaMemcpyHostToDevice, d->stream));
+  rc = ensure_pipeline(d);
+  if (rc) return rc;
+  int i = 0;
+  for (int64_t off = 0; off < nframes; off += slice, ++i) {
+    const int nf = (int)std::min<int64_t>(slice, nframes - off);
+    const int b = i & 1;
+    uint8_t* base = (uint8_t*)d->stage + (size_t)b * one;
+    uint32_t* its = (uint32_t*)base;          // [nf][2], kept first for alignment
+    uint8_t* inX = base + it_bytes;
+    uint8_t* inZ = inX + (size_t)mX * nf;
+    uint8_t* oX = base + it_bytes + in_bytes;
+    uint8_t* oZ = oX + (size_t)n * nf;
+    uint8_t* oF = oZ + (size_t)n * nf;
+    if (i >= 2) CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_free[b], 0));
+    CU_TRY(cudaMemcpyAsync(inX, synX + off * mX, (size_t)nf * mX, cudaMemcpyHostToDevice, d->copy_stream));
+    CU_TRY(cudaMemcpyAsync(inZ, synZ + off * mZ, (size_t)nf * mZ, cudaMemcpyHostToDevice, d->copy_stream));
+    CU_TRY(cudaEventRecord(d->ev_ready[b], d->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_ready[b], 0));
     {
       Timed t(d, QLDPC_T_PACK, 2);
-      CU_TRY(launch_pack(st0, 1, nf, mX, d->s[0].mw, d->synX, d->stream));
-      CU_TRY(launch_pack(st1, 1, nf, mZ, d->s[1].mw, d->synZ, d->stream));
+      CU_TRY(launch_pack(inX, 1, nf, mX, d->s[0].mw, d->synX, d->stream));
+      CU_TRY(launch_pack(inZ, 1, nf, mZ, d->s[1].mw, d->synZ, d->stream));
     }
+    CU_TRY(cudaEventRecord(d->ev_free[b], d->stream));
     rc = run_bp(d, d->synX, d->synZ, nf, errorProbability, maxIterations, d->decX, d->decZ, d->sfX, d->sfZ, d->itX, d->itZ);
     if (rc) return rc;
+    if (i >= 2) CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_out_free[b], 0));
     {
       Timed t(d, QLDPC_T_PACK, 3);
-      CU_TRY(launch_unpack(d->decX, nf, n, d->nw, st0, d->stream));
-      CU_TRY(launch_unpack(d->decZ, nf, n, d->nw, st1, d->stream));
-      CU_TRY(launch_merge_flags(d->sfX, d->sfZ, nf, d->fflags, d->stream));
+      CU_TRY(launch_unpack(d->decX, nf, n, d->nw, oX, d->stream));
+      CU_TRY(launch_unpack(d->decZ, nf, n, d->nw, oZ, d->stream));
+      CU_TRY(launch_merge_flags(d->sfX, d->sfZ, nf, oF, d->stream));
     }
-    CU_TRY(cudaMemcpyAsync(outX + off * n, st0, (size_t)nf * n, cudaMemcpyDeviceToHost, d->stream));
-    CU_TRY(cudaMemcpyAsync(outZ + off * n, st1, (size_t)nf * n, cudaMemcpyDeviceToHost, d->stream));
-    CU_TRY(cudaMemcpyAsync(outFlags + off, d->fflags, (size_t)nf, cudaMemcpyDeviceToHost, d->stream));
     if (outIters) {
-      CU_TRY(cudaMemcpy2DAsync(outIters + 2 * off, 8, d->itX, 4, 4, (size_t)nf, cudaMemcpyDeviceToHost, d->stream));
-      CU_TRY(cudaMemcpy2DAsync(outIters + 2 * off + 1, 8, d->itZ, 4, 4, (size_t)nf, cudaMemcpyDeviceToHost, d->stream));
+      CU_TRY(cudaMemcpy2DAsync(its, 8, d->itX, 4, 4, (size_t)nf, cudaMemcpyDeviceToDevice, d->stream));
+      CU_TRY(cudaMemcpy2DAsync(its + 1, 8, d->itZ, 4, 4, (size_t)nf, cudaMemcpyDeviceToDevice, d->stream));
     }
-    CU_TRY(cudaStreamSynchronize(d->stream));
+    CU_TRY(cudaEventRecord(d->ev_done[b], d->stream));
+    CU_TRY(cudaStreamWaitEvent(d->d2h_stream, d->ev_done[b], 0));
+    CU_TRY(cudaMemcpyAsync(outX + off * n, oX, (size_t)nf * n, cudaMemcpyDeviceToHost, d->d2h_stream));
+    CU_TRY(cudaMemcpyAsync(outZ + off * n, oZ, (size_t)nf * n, cudaMemcpyDeviceToHost, d->d2h_stream));
+    CU_TRY(cudaMemcpyAsync(outFlags + off, oF, (size_t)nf, cudaMemcpyDeviceToHost, d->d2h_stream));
+    if (outIters)
+      CU_TRY(cudaMemcpyAsync(outIters + 2 * off, its, (size_t)nf * 8, cudaMemcpyDeviceToHost, d->d2h_stream));
+    CU_TRY(cudaEventRecord(d->ev_out_free[b], d->d2h_stream));
   }
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  CU_TRY(cudaStreamSynchronize(d->d2h_stream));
   return QLDPC_OK;
 }
 
@@ -784,8 +833,6 @@ int qldpc_get_statistics_weightw(qldpc_decoder* dec, int errorWeight, int64_t nu
 // Host-supplied error patterns are processed in slices of at most kPipeFrames frames: slice i+1 is copied to the device
 // on a second stream while slice i is packed, decoded and reduced (two staging buffers, events for hand-over), so
 // with pinned host memory the PCIe transfer hides behind the decode (or vice versa).
-static const int kPipeFrames = 1 << 17;
-
 static int stats_from_errors(qldpc_decoder* d, const void* xErrors, const void* zErrors, int elem, int64_t numErrors,
                              float errorProbability, int maxIterations, uint64_t* counters, uint8_t* perFrameFlags,
                              uint32_t* perFrameIters) {
@@ -798,13 +845,8 @@ static int stats_from_errors(qldpc_decoder* d, const void* xErrors, const void* 
   const size_t half = 2 * row * (size_t)slice;  // one staging buffer: x rows then z rows
   rc = ensure_stage(d, 2 * half);
   if (rc) return rc;
-  if (!d->copy_stream) {
-    CU_TRY(cudaStreamCreateWithFlags(&d->copy_stream, cudaStreamNonBlocking));
-    for (int i = 0; i < 2; ++i) {
-      CU_TRY(cudaEventCreateWithFlags(&d->ev_ready[i], cudaEventDisableTiming));
-      CU_TRY(cudaEventCreateWithFlags(&d->ev_free[i], cudaEventDisableTiming));
-    }
-  }
+  rc = ensure_pipeline(d);
+  if (rc) return rc;
   CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
   int i = 0;
   for (int64_t off = 0; off < numErrors; off += slice, ++i) {
