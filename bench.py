@@ -332,6 +332,9 @@ def run_native(args):
             "e2e": {"value": F * n_gpus * args.steps / e2e_s, "unit": "frames/s",
                     "h2d_bytes_per_step": 2 * F * n * 4, "d2h_bytes_per_step": q.NUM_COUNTERS * 8,
                     "api": "qldpc_get_stats_from_errors_i32 (DecoderGPU::GetStats layout, pinned host int32)",
+                    "note": "the reference's layout spends one int32 per qubit (4880 B per frame): this number is "
+                            "bound by the H2D link (about 51 GB/s per GPU, about 200 GB/s of host memory traffic per "
+                            "box), not by the decoder; u8_patterns and device_generated show the other two entry points",
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "u8_patterns": {"value": F * n_gpus * args.steps / e2e_u8_s, "unit": "frames/s",
                                     "h2d_bytes_per_step": 2 * F * n, "api": "qldpc_get_stats_from_errors_u8"},
