@@ -301,6 +301,24 @@ def test_global_memory_path_matches_oracle(qldpc, oracle, code, nf):
     assert np.array_equal(dec.get_statistics_depolarizing(77, 3, nf, p, maxit)["counters"], b["counters"])
 
 
+@pytest.mark.parametrize("prm,shapes", [((3, 4, 8, 13, 5, 2), ((8, 3), (8, 4))), ((6, 6, 12, 7, 3, 2), ((12, 6), (12, 6)))])
+def test_other_instantiated_shapes(qldpc, oracle, prm, shapes):
+    """The remaining compiled (check degree, variable degree) instantiations of the tile kernel, all tile widths."""
+    gc = qldpc.Code.qc(*prm)
+    assert ((gc.dcX, gc.dvX), (gc.dcZ, gc.dvZ)) == shapes
+    dec = qldpc.Decoder(gc, 0, 4096)
+    oc = oracle.code_qc(*prm)
+    oc.set_logical(gc.dense_matrix(2))
+    b = oc.run_depolarizing(9, 0, 3000, 0.03, 30)
+    for vec in (0, 4, 2, 1):
+        for side in (0, 1):
+            dec.configure(side, vec, 0, 0)
+            assert dec.launch_info(side)["vec"] in (1, 2, 4)
+        a = dec.get_statistics_depolarizing(9, 0, 3000, 0.03, 30, per_frame=True)
+        assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
+        assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))
+
+
 @pytest.mark.parametrize("prm,maxit", [((2, 2, 4, 11, 10, 2), 25), ((3, 4, 14, 13, 3, 2), 31)])
 def test_shapes_without_tile_kernel_use_global_path(qldpc, oracle, prm, maxit):
     """(check degree, variable degree) pairs with no compiled tile kernel decode through the global-memory path."""
