@@ -34,7 +34,10 @@ def main():
     ap.add_argument("--code", default=None, help="code file in the reference's 4-line format")
     ap.add_argument("--qc", default="4,5,10,61,9,49", help="J,K,L,P,sigma,tau when no --code is given")
     ap.add_argument("--p", default="0.01:0.10:10", help="lo:hi:points (inclusive, linear) or a comma list")
-    ap.add_argument("--frames", type=int, default=1_000_000, help="frames per p-point (whole job)")
+    ap.add_argument("--frames", type=int, default=1_000_000, help="frames per p-point and batch (whole job)")
+    ap.add_argument("--target-errors", type=int, default=0,
+                    help="stopping rule: keep adding batches of --frames until this many frame errors were seen (0 = one batch)")
+    ap.add_argument("--max-frames", type=int, default=100_000_000, help="cap on frames per p-point under --target-errors")
     ap.add_argument("--max-iterations", type=int, default=50)
     ap.add_argument("--seed", type=int, default=20261018)
     args = ap.parse_args()
@@ -61,8 +64,14 @@ def main():
     for i, p in enumerate(ps):
         p = float(np.float32(p))
         t0 = time.perf_counter()
-        k = run_sharded(lambda first, n: dec.get_statistics_depolarizing(args.seed + i, first, n, p, args.max_iterations)[
-            "counters"], args.frames, device="cuda")
+        k = np.zeros(q.NUM_COUNTERS, np.uint64)
+        while True:  # batches continue the same global frame-id stream, so the result does not depend on the batching
+            done = int(k[0])
+            k += run_sharded(lambda first, n: dec.get_statistics_depolarizing(args.seed + i, first, n, p,
+                                                                              args.max_iterations)["counters"],
+                             args.frames, first_frame=done, device="cuda")
+            if int(k[0]) - int(k[3]) >= args.target_errors or int(k[0]) >= args.max_frames or args.target_errors <= 0:
+                break
         torch.cuda.synchronize()
         sec = allreduce_max(time.perf_counter() - t0, "cuda")
         if rank == 0:
