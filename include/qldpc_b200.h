@@ -117,7 +117,8 @@ void qldpc_decoder_destroy(qldpc_decoder* dec);
 int qldpc_decoder_set_stream(qldpc_decoder* dec, void* cuda_stream);
 /* Tuning knobs (0 = heuristic): frames per CTA tile (1, 2 or 4) and threads per CTA for side 0/1.
  * frames_per_tile = -1 selects the global-memory (HBM-resident) BP path, which is otherwise used only for shapes the
- * shared-memory tile kernel does not cover (no instantiation for the degrees, or a frame larger than shared memory). */
+ * shared-memory tile kernel does not cover (no instantiation for the degrees, or a frame larger than shared memory);
+ * with -1, threads_per_cta is the number of frame slots kept in flight (0 = heuristic) and ctas_per_sm is ignored. */
 int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, int threads_per_cta, int ctas_per_sm);
 /* Launch geometry in use: out[0..7] = vec (-1: global-memory path), threads, ctas_per_sm, grid, dyn_smem_bytes, regs,
  * SM count, frames per launch. */

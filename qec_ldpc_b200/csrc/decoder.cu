@@ -310,6 +310,7 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
       GlobalBpArgs g;
       g.m = s.m; g.n = d->n; g.dc = s.dc; g.dv = s.dv; g.mw = s.mw; g.nw = d->nw;
       g.maxit = maxIterations; g.batch = s.gbatch; g.prior = prior;
+      g.slots = s.force_global ? s.user.threads : 0;
       g.vrow = s.gvrow; g.cvar = s.gcvar; g.msg = s.gmsg; g.bytes = s.gbytes; g.words = s.gwords;
       CU_TRY(global_bp_run(g, a.syn, a.dec, a.flags, a.iters, nf, nullptr, d->stream));
       continue;

@@ -26,12 +26,13 @@ cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, i
 // Global-memory fallback path (bp_global.cu).
 struct GlobalBpArgs {
   int m, n, dc, dv, mw, nw, maxit, batch;
+  int slots = 0;         // frame slots in flight (0 = heuristic), at most `batch`
   float prior;
   const uint32_t* vrow;  // [dv][n]
   const uint32_t* cvar;  // [dc][m]
   float* msg;            // [E][batch]
-  uint8_t* bytes;        // syndrome bytes [m][batch] + 5 per-frame byte arrays
-  uint32_t* words;       // iteration counts [batch] + a counter
+  uint8_t* bytes;        // syndrome bytes [m][batch] + 4 per-slot byte arrays
+  uint32_t* words;       // frame ids [batch], iteration indices [batch], 2 counters
 };
 size_t global_bp_bytes(int m, int dc, int batch, size_t* msg_bytes, size_t* byte_bytes, size_t* word_bytes);
 cudaError_t global_bp_run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8_t* flags, uint32_t* iters,

@@ -296,6 +296,13 @@ def test_global_memory_path_matches_oracle(qldpc, oracle, code, nf):
     b = oc.run_depolarizing(77, 3, nf, p, maxit)
     assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
     assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))
+    # few slots in flight: every slot is handed a new frame many times (the refill path), result unchanged
+    for slots in (32, 96):
+        for side in (0, 1):
+            dec.configure(side, -1, slots, 0)
+        a = dec.get_statistics_depolarizing(77, 3, nf, p, maxit, per_frame=True)
+        assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
+        assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))
     for side in (0, 1):
         dec.configure(side, 0, 0, 0)
     assert np.array_equal(dec.get_statistics_depolarizing(77, 3, nf, p, maxit)["counters"], b["counters"])
@@ -327,7 +334,10 @@ def test_shapes_without_tile_kernel_use_global_path(qldpc, oracle, prm, maxit):
     assert dec.launch_info(0)["vec"] == -1
     oc = oracle.code_qc(*prm)
     oc.set_logical(gc.dense_matrix(2))
-    a = dec.get_statistics_depolarizing(5, 0, 2500, 0.04, maxit, per_frame=True)
     b = oc.run_depolarizing(5, 0, 2500, 0.04, maxit)
-    assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
-    assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))
+    for slots in (0, 64):  # heuristic (all frames in flight at once) and a small slot pool that is refilled ~40 times
+        for side in (0, 1):
+            dec.configure(side, -1, slots, 0)
+        a = dec.get_statistics_depolarizing(5, 0, 2500, 0.04, maxit, per_frame=True)
+        assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
+        assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))

@@ -3,6 +3,7 @@
   C1  J3K3L6P7   p=0.05  20 iterations   (the reference's CPU-sized case)
   C4  J4K5L10P61 p=0.01 200 iterations   (early-exit divergence: almost all frames stop at 11, stragglers run to 200)
   C5  J4K4L8P509 p=0.03  50 iterations   (large code: one frame-side = 65 KB of messages, still shared-memory resident)
+A name with a trailing "g" (C5g, C2g) forces the HBM-resident path (bp_global.cu) on the same configuration.
 One JSON line per configuration: frames/s, edge-updates/s, mean iterations, roofline fractions, launch shapes."""
 import json
 import os
@@ -23,9 +24,13 @@ def main():
     peaks = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "MEASURED_PEAKS.json")
     hbm = float(json.load(open(peaks))["hbm_gbs"]) if os.path.exists(peaks) else 6650.0
     for name in names:
-        prm, p, maxit, frames = CONFIGS[name]
+        forced_global = name.endswith("g")
+        prm, p, maxit, frames = CONFIGS[name.rstrip("g")]
         code = q.Code.qc(*prm)
         dec = q.Decoder(code, 0, frames)
+        if forced_global:
+            for side in (0, 1):
+                dec.configure(side, -1, 0, 0)
         stream = torch.cuda.Stream()
         dec.set_stream(stream.cuda_stream)
         for s in range(3):

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
 """Randomised differential run: CUDA path vs CPU oracle, frame by frame, over many (code, p, max iterations, seed)
-combinations and every tile width.  Prints one line per case; exits non-zero on the first disagreement."""
+combinations, every tile width and the HBM-resident path with random slot-pool sizes (vec=-1).  Prints one line per case; exits non-zero on the first disagreement."""
 import sys
 import time
 
@@ -31,10 +31,11 @@ while time.time() < t_end:
     nf = {"C1": 20000, "C2": 4000, "C5": 300}[name]
     seed = int(rng.integers(0, 2**62))
     first = int(rng.integers(0, 2**40))
-    vec = int(rng.choice([0, 4, 2, 1]))
+    vec = int(rng.choice([0, 4, 2, 1, -1]))
+    slots = int(rng.choice([0, 32, 64, 256, 1024])) if vec < 0 else 0
     for side in (0, 1):
         try:
-            dec.configure(side, vec, 0, 0)
+            dec.configure(side, vec, slots, 0)
         except q.QldpcError:
             dec.configure(side, 0, 0, 0)
     a = dec.get_statistics_depolarizing(seed, first, nf, p, maxit, per_frame=True)
