@@ -4,14 +4,18 @@
 // and the reference (EqNodeUpdate / VarNodeUpdate / CheckConvergence / Decode tail, DecoderCPU.h:150-390); only
 // the residence of the message state differs.
 //
-// Layout: msg[row][S] with row = i*m + e (i = position of the edge in its check) and the SLOT index innermost, so a
-// warp that processes one node for 32 consecutive slots reads and writes fully coalesced 128-byte lines: the path is
-// bound by HBM at 16 bytes per edge-update.  S frame slots are decoded concurrently.  Like the tile
-// kernel, every slot has its own iteration counter, n % 10 convergence cadence and `last` iteration; a slot that stops
-// is hard-decided, syndrome-checked, written out and refilled from a frame queue in the same pass, so slots never idle
-// while frames remain (no lock-step batches).  One pass = check kernel, variable kernel, and four small kernels that
-// only touch the slots which just stopped.  Degrees are runtime values up to 32; the kernels are
-// instantiated for a ladder of degree bounds and W = 4, 2 or 1 slots per thread.
+// Layout: msg[row][S] with row = i*m + e (i = position of the edge in its check) and the SLOT index innermost; a
+// thread handles one node for W (4, 2 or 1) consecutive slots with one 4*W-byte access per message row, so a warp
+// moves up to 512 contiguous bytes per row and the path is bound by HBM at 16 bytes per edge-update.
+// S frame slots are decoded concurrently.  Like the tile kernel, every slot has its own iteration counter, n % 10
+// convergence cadence and `last` iteration; a slot that stops is syndrome-checked, written out and handed the next
+// frame of a queue in the same pass, so slots never idle while frames remain (no lock-step batches).
+//
+// One pass = g_check, g_var (+ its last-iteration variant), g_control, then the kernels that serve the slots which
+// just stopped: g_verify, g_pack, g_handover, g_fill.  Everything a stopped slot needs is produced in slot-innermost
+// arrays by the passes themselves (the variable kernel writes the hard decision of every slot that is at a
+// convergence checkpoint, one byte per variable), so these kernels stay coalesced even though the stopped slots are
+// scattered; a fresh slot is not initialised at all -- its first check phase substitutes the prior for the messages.
 #include <algorithm>
 #include <cstdint>
 
@@ -21,28 +25,36 @@ namespace qldpc {
 
 namespace {
 
+// kFresh = running its iteration 0: the messages are implicitly the prior (InitVarNodes, DecoderCPU.h:135-148)
 enum : uint8_t { kIdle = 0, kRun = 1, kDone = 2, kFresh = 3 };
+__device__ __forceinline__ bool running(uint8_t st) { return st == kRun || st == kFresh; }
+
+constexpr int kGroup = 256;  // slots per control block = granularity of the `lastflag` hints
 
 struct Slots {
   float* msg;          // [E][S]
   uint8_t* synb;       // [m][S] input syndrome bit of the frame in the slot
-  uint8_t* state;      // [S] kIdle / kRun / kDone / kFresh
+  uint8_t* state;      // [S]
   uint8_t* bad;        // [S] an unconverged message was seen in the last variable phase
-  uint8_t* nanflag;    // [S]
+  uint8_t* nanflag;    // [S] a NaN message was seen in the last checkpoint variable phase
   uint8_t* mismatch;   // [S]
+  uint8_t* decb;       // [n][S] hard decision after the last checkpoint variable phase, one byte per bit
   int32_t* frame;      // [S] frame id in the slot
   int32_t* iter;       // [S] iteration index n of the slot
   unsigned int* ctr;   // [0] next frame to hand out, [1] frames completed
+  uint32_t* lastflag;  // [ceil(S / kGroup)] some slot of the group is in its last iteration in the coming pass
 };
 
-// Slots start as kDone-less kFresh candidates: every slot asks the queue for its first frame.
-__global__ void __launch_bounds__(256) g_start(Slots s, int S) {
+// Every slot starts "stopped" with no frame to write out: g_handover gives it its first frame.
+__global__ void __launch_bounds__(kGroup) g_start(Slots s, int S) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
   if (t < S) {
-    s.state[t] = kDone;   // "stopped" with no frame to write out: g_handover gives it its first frame
+    s.state[t] = kDone;
     s.frame[t] = -1;
+    s.iter[t] = 0;
     s.bad[t] = s.nanflag[t] = s.mismatch[t] = 0;
   }
+  if (threadIdx.x == 0) s.lastflag[blockIdx.x] = 0;
   if (t < 2) s.ctr[t] = 0;
 }
 
@@ -69,19 +81,28 @@ template <int W> __device__ __forceinline__ void ld_i(int (&d)[W], const int32_t
   else d[0] = p[0];
 }
 
+template <int W> __device__ __forceinline__ void st_b(uint8_t* p, const uint8_t (&d)[W]) {
+  if constexpr (W == 4) *reinterpret_cast<uchar4*>(p) = make_uchar4(d[0], d[1], d[2], d[3]);
+  else if constexpr (W == 2) *reinterpret_cast<uchar2*>(p) = make_uchar2(d[0], d[1]);
+  else p[0] = d[0];
+}
+
 // A thread whose W slots are not all running still computes and stores all W lanes: the other lanes are idle slots
-// (stopped and fresh slots only exist between g_control and g_activate), whose messages nobody reads.
+// (stopped slots only exist between g_control and g_handover), whose messages nobody reads.
 template <int MAXC, int W, bool EXACT>
-__global__ void __launch_bounds__(128) g_check(Slots s, int m, int dc_rt, int S) {
+__global__ void __launch_bounds__(128) g_check(Slots s, int m, int dc_rt, int S, float prior) {
   const int dc = EXACT ? MAXC : dc_rt;
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) * W;
   const int e = blockIdx.y;
   if (f >= S) return;
   uint8_t st[W];
   ld_b<W>(st, s.state + f);
-  bool any = false;
+  bool any = false, anyfresh = false;
 #pragma unroll
-  for (int w = 0; w < W; ++w) any |= st[w] == kRun;
+  for (int w = 0; w < W; ++w) {
+    any |= running(st[w]);
+    anyfresh |= st[w] == kFresh;
+  }
   if (!any) return;
   float t[MAXC][W];
 #pragma unroll
@@ -91,6 +112,16 @@ __global__ void __launch_bounds__(128) g_check(Slots s, int m, int dc_rt, int S)
 #pragma unroll
       for (int w = 0; w < W; ++w) t[i][w] = __fmaf_rn(-2.0f, t[i][w], 1.0f);  // 1 - 2q (DecoderCPU.h:175)
     }
+  if (anyfresh) {
+    const float tp = __fmaf_rn(-2.0f, prior, 1.0f);
+#pragma unroll
+    for (int i = 0; i < MAXC; ++i)
+      if (i < dc) {
+#pragma unroll
+        for (int w = 0; w < W; ++w)
+          if (st[w] == kFresh) t[i][w] = tp;
+      }
+  }
   uint8_t sb[W];
   ld_b<W>(sb, s.synb + (size_t)e * S + f);
   float cf[W], pre[W];
@@ -121,58 +152,70 @@ __global__ void __launch_bounds__(128) g_check(Slots s, int m, int dc_rt, int S)
   }
 }
 
-template <int MAXV, int W, bool EXACT>
+// Two launches per pass: LAST = false serves the threads none of whose slots is in its final iteration (no
+// full-product registers: higher occupancy for a bandwidth-bound kernel), LAST = true the others (DecoderCPU.h:284);
+// the latter first consults the per-group hints g_control left and normally retires at once.
+template <int MAXV, int W, bool EXACT, bool LAST>
 __global__ void __launch_bounds__(128) g_var(Slots s, const uint32_t* __restrict__ vrow, int n, int dv_rt, int S,
                                              float prior, int last_it) {
   const int dv = EXACT ? MAXV : dv_rt;
+  if (LAST) {
+    const int lo = blockIdx.x * (128 * W) / kGroup, hi = min((S - 1) / kGroup, ((blockIdx.x + 1) * (128 * W) - 1) / kGroup);
+    uint32_t hint = 0;
+    for (int g = lo; g <= hi; ++g) hint |= s.lastflag[g];
+    if (!hint) return;
+  }
   const int f = (blockIdx.x * blockDim.x + threadIdx.x) * W;
   const int v = blockIdx.y;
   if (f >= S) return;
   uint8_t st[W];
   ld_b<W>(st, s.state + f);
-  bool any = false;
-#pragma unroll
-  for (int w = 0; w < W; ++w) any |= st[w] == kRun;
-  if (!any) return;
   int it[W];
   ld_i<W>(it, s.iter + f);
-  bool last[W], anylast = false;
+  bool any = false, anylast = false, anyck = false, last[W], ck[W];
 #pragma unroll
   for (int w = 0; w < W; ++w) {
-    last[w] = it[w] == last_it;  // DecoderCPU.h:284,287
+    const bool run = running(st[w]);
+    last[w] = run && it[w] == last_it;              // DecoderCPU.h:284
+    ck[w] = run && (last[w] || it[w] % 10 == 0);    // DecoderCPU.h:287
+    any |= run;
     anylast |= last[w];
+    anyck |= ck[w];
   }
-  float pk[MAXV][W], om[MAXV][W];
+  if (!any || anylast != LAST) return;
+  // Only the messages are kept in registers; the complements 1 - p are recomputed where they are used (one FADD,
+  // same rounding), which is cheaper than the occupancy their registers would cost a bandwidth-bound kernel.
+  float pk[MAXV][W];
   uint32_t row[MAXV];
 #pragma unroll
   for (int k = 0; k < MAXV; ++k)
     if (k < dv) {
       row[k] = vrow[(size_t)k * n + v];
       ld_f<W>(pk[k], s.msg + (size_t)row[k] * S + f);
-#pragma unroll
-      for (int w = 0; w < W; ++w) om[k][w] = __fsub_rn(1.0f, pk[k][w]);
     }
   const float prior1 = __fsub_rn(1.0f, prior);  // DecoderCPU.h:209-210
-  float preP[W], preQ[W], fullP[W], fullQ[W];
+  float preP[W], preQ[W], fullP[LAST ? W : 1], fullQ[LAST ? W : 1];
 #pragma unroll
   for (int w = 0; w < W; ++w) {
-    preP[w] = fullP[w] = prior;
-    preQ[w] = fullQ[w] = prior1;
+    preP[w] = prior;
+    preQ[w] = prior1;
+    if (LAST) { fullP[w] = prior; fullQ[w] = prior1; }
   }
-  if (anylast) {
+  if (LAST) {
 #pragma unroll
     for (int k = 0; k < MAXV; ++k)
       if (k < dv) {
 #pragma unroll
         for (int w = 0; w < W; ++w) {
-          fullQ[w] = __fmul_rn(fullQ[w], om[k][w]);
+          fullQ[w] = __fmul_rn(fullQ[w], __fsub_rn(1.0f, pk[k][w]));
           fullP[w] = __fmul_rn(fullP[w], pk[k][w]);
         }
       }
   }
-  bool anybad[W];
+  bool anybad[W], anynan[W];
+  uint8_t bit[W];
 #pragma unroll
-  for (int w = 0; w < W; ++w) anybad[w] = false;
+  for (int w = 0; w < W; ++w) { anybad[w] = anynan[w] = false; bit[w] = 0; }
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
     if (j < dv) {
@@ -184,86 +227,111 @@ __global__ void __launch_bounds__(128) g_var(Slots s, const uint32_t* __restrict
         if (k < dv) {
 #pragma unroll
           for (int w = 0; w < W; ++w) {
-            Q[w] = __fmul_rn(Q[w], om[k][w]);
+            Q[w] = __fmul_rn(Q[w], __fsub_rn(1.0f, pk[k][w]));
             P[w] = __fmul_rn(P[w], pk[k][w]);
           }
         }
       float q[W];
 #pragma unroll
       for (int w = 0; w < W; ++w) {
-        if (last[w]) { P[w] = fullP[w]; Q[w] = fullQ[w]; }
+        if (LAST && last[w]) { P[w] = fullP[w]; Q[w] = fullQ[w]; }
         const float den = __fadd_rn(Q[w], P[w]);
         bool unsafe = false;
         q[w] = div_fast<3>(P[w], den, unsafe);  // == P / (Q + P), DecoderCPU.h:223
         if (unsafe) q[w] = __fdiv_rn(P[w], den);
         anybad[w] |= unconverged(q[w]);
-        preQ[w] = __fmul_rn(preQ[w], om[j][w]);
+        anynan[w] |= q[w] != q[w];
+        bit[w] |= q[w] >= 0.5f;  // hard decision: any edge message >= 0.5f (DecoderCPU.h:354-373)
+        preQ[w] = __fmul_rn(preQ[w], __fsub_rn(1.0f, pk[j][w]));
         preP[w] = __fmul_rn(preP[w], pk[j][w]);
       }
       st_f<W>(s.msg + (size_t)row[j] * S + f, q);
     }
   }
+  if (!anyck) return;
+  // A slot can only stop at a checkpoint, so this is where its decision is recorded (lanes that are not at one get
+  // a value nobody reads).
+  st_b<W>(s.decb + (size_t)v * S + f, bit);
 #pragma unroll
   for (int w = 0; w < W; ++w)
-    if (st[w] == kRun && (last[w] || it[w] % 10 == 0) && anybad[w]) s.bad[f + w] = 1;
+    if (ck[w]) {
+      if (anybad[w]) s.bad[f + w] = 1;
+      if (anynan[w]) s.nanflag[f + w] = 1;
+    }
 }
 
 // BeliefPropogation loop control (DecoderCPU.h:280-291), per slot, after the variable phase.
-__global__ void __launch_bounds__(256) g_control(Slots s, int S, int last_it) {
+__global__ void __launch_bounds__(kGroup) g_control(Slots s, int S, int last_it) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= S || s.state[f] != kRun) return;
-  const int it = s.iter[f];
-  const bool last = it == last_it, ck = last || it % 10 == 0;
-  if (last || (ck && !s.bad[f])) s.state[f] = kDone;  // bad[f] is kept: CONVERGENCE_FAIL of the final state
-  else {
-    s.iter[f] = it + 1;
-    s.bad[f] = 0;
-  }
-}
-
-// The three kernels below only work for slots that stopped in this pass; blockIdx.y strides over the nodes so that a
-// warp without such a slot retires after one byte load.
-
-// hard decision (any edge message >= 0.5f, DecoderCPU.h:354-373) + NaN flag
-__global__ void __launch_bounds__(128) g_decide(Slots s, const uint32_t* __restrict__ vrow, int n, int dv, int S, int nw,
-                                                uint32_t* __restrict__ dec) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= S || s.state[f] != kDone || s.frame[f] < 0) return;
-  uint32_t* d = dec + (size_t)s.frame[f] * nw;
-  bool nan = false;
-  for (int v = blockIdx.y; v < n; v += gridDim.y) {
-    bool bit = false;
-    for (int k = 0; k < dv; ++k) {
-      const float x = s.msg[(size_t)vrow[(size_t)k * n + v] * S + f];
-      bit |= x >= 0.5f;
-      nan |= x != x;
+  int next_is_last = 0;
+  if (f < S && running(s.state[f])) {
+    const int it = s.iter[f];
+    const bool last = it == last_it, ck = last || it % 10 == 0;
+    if (last || (ck && !s.bad[f])) {
+      s.state[f] = kDone;  // bad / nanflag are kept: CONVERGENCE_FAIL and the NaN bit describe the final state
+    } else {
+      s.state[f] = kRun;
+      s.iter[f] = it + 1;
+      s.bad[f] = s.nanflag[f] = 0;
+      next_is_last = it + 1 == last_it;
     }
-    if (bit) atomicOr(&d[v >> 5], 1u << (v & 31));
   }
-  if (nan) s.nanflag[f] = 1;
+  next_is_last = __syncthreads_or(next_is_last);
+  if (threadIdx.x == 0) s.lastflag[blockIdx.x] = next_is_last;
 }
 
-// syndrome of the decision against the input syndrome (DecoderCPU.h:380-384)
-__global__ void __launch_bounds__(128) g_verify(Slots s, const uint32_t* __restrict__ cvar, int m, int dc, int S, int nw,
-                                                const uint32_t* __restrict__ dec) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= S || s.state[f] != kDone || s.frame[f] < 0) return;
-  const uint32_t* d = dec + (size_t)s.frame[f] * nw;
+// syndrome of the decision against the input syndrome (DecoderCPU.h:380-384), for the slots that just stopped
+__global__ void __launch_bounds__(128) g_verify(Slots s, const uint32_t* __restrict__ cvar, int m, int dc, int S) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (f >= S) return;
+  uint8_t st[4];
+  ld_b<4>(st, s.state + f);
+  if (st[0] != kDone && st[1] != kDone && st[2] != kDone && st[3] != kDone) return;
   unsigned any = 0;
   for (int e = blockIdx.y; e < m; e += gridDim.y) {
-    unsigned par = s.synb[(size_t)e * S + f];
-    for (int i = 0; i < dc; ++i) {
-      const uint32_t v = cvar[(size_t)i * m + e];
-      par ^= (d[v >> 5] >> (v & 31)) & 1u;
-    }
+    unsigned par = *reinterpret_cast<const uint32_t*>(s.synb + (size_t)e * S + f);  // 4 slots, one byte each
+    for (int i = 0; i < dc; ++i)
+      par ^= *reinterpret_cast<const uint32_t*>(s.decb + (size_t)cvar[(size_t)i * m + e] * S + f);
     any |= par;
   }
-  if (any) s.mismatch[f] = 1;
+#pragma unroll
+  for (int w = 0; w < 4; ++w)
+    if (st[w] == kDone && ((any >> (8 * w)) & 1u)) s.mismatch[f + w] = 1;
+}
+
+// decision bytes -> bit-packed words of the frame, for the slots that just stopped
+__global__ void __launch_bounds__(128) g_pack(Slots s, int n, int S, int nw, uint32_t* __restrict__ dec) {
+  const int f = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
+  if (f >= S) return;
+  uint8_t st[4];
+  ld_b<4>(st, s.state + f);
+  int fr[4];
+  ld_i<4>(fr, s.frame + f);
+  bool any = false;
+#pragma unroll
+  for (int w = 0; w < 4; ++w) {
+    if (st[w] != kDone) fr[w] = -1;
+    any |= fr[w] >= 0;
+  }
+  if (!any) return;
+  for (int word = blockIdx.y; word < nw; word += gridDim.y) {
+    uint32_t out[4] = {0, 0, 0, 0};
+    for (int b = 0; b < 32; ++b) {
+      const int v = word * 32 + b;
+      if (v >= n) break;
+      const uint32_t d = *reinterpret_cast<const uint32_t*>(s.decb + (size_t)v * S + f);
+#pragma unroll
+      for (int w = 0; w < 4; ++w) out[w] |= ((d >> (8 * w)) & 1u) << b;
+    }
+#pragma unroll
+    for (int w = 0; w < 4; ++w)
+      if (fr[w] >= 0) dec[(size_t)fr[w] * nw + word] = out[w];
+  }
 }
 
 // per-frame outputs of the stopped slots, then the hand-over to the next frame of the queue
-__global__ void __launch_bounds__(256) g_handover(Slots s, int S, int nframes, uint8_t* __restrict__ flags,
-                                                  uint32_t* __restrict__ iters) {
+__global__ void __launch_bounds__(kGroup) g_handover(Slots s, int S, int nframes, int last_it, uint8_t* __restrict__ flags,
+                                                     uint32_t* __restrict__ iters) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= S || s.state[f] != kDone) return;
   const int fr = s.frame[f];
@@ -279,30 +347,23 @@ __global__ void __launch_bounds__(256) g_handover(Slots s, int S, int nframes, u
   if (next < (unsigned)nframes) {
     s.frame[f] = (int)next;
     s.state[f] = kFresh;
+    if (last_it == 0) s.lastflag[blockIdx.x] = 1;  // a one-iteration run: the first iteration is the last
   } else {
     s.frame[f] = -1;
     s.state[f] = kIdle;
   }
 }
 
-// fresh slots: messages <- prior (InitVarNodes, DecoderCPU.h:135-148), syndrome bits -> bytes
-__global__ void __launch_bounds__(128) g_fill(Slots s, const uint32_t* __restrict__ syn, int mw, int m, int E, int S,
-                                              float prior) {
+// syndrome bits of the frames just handed out -> one byte per (check, slot).  Runs right after g_handover, when
+// kFresh marks exactly the new arrivals (g_control turns kFresh into kRun after their first iteration).
+__global__ void __launch_bounds__(128) g_fill(Slots s, const uint32_t* __restrict__ syn, int mw, int m, int S) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= S || s.state[f] != kFresh) return;
-  const int fr = s.frame[f];
-  for (int r = blockIdx.y; r < E; r += gridDim.y) {
-    s.msg[(size_t)r * S + f] = prior;
-    if (r < m) s.synb[(size_t)r * S + f] = (uint8_t)((syn[(size_t)fr * mw + (r >> 5)] >> (r & 31)) & 1u);
-  }
+  const uint32_t* row = syn + (size_t)s.frame[f] * mw;
+  for (int e = blockIdx.y; e < m; e += gridDim.y) s.synb[(size_t)e * S + f] = (uint8_t)((row[e >> 5] >> (e & 31)) & 1u);
 }
 
-__global__ void __launch_bounds__(256) g_activate(Slots s, int S) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f < S && s.state[f] == kFresh) s.state[f] = kRun;
-}
-
-using CheckFn = void (*)(Slots, int, int, int);
+using CheckFn = void (*)(Slots, int, int, int, float);
 using VarFn = void (*)(Slots, const uint32_t*, int, int, int, float, int);
 constexpr int check_width(int maxc) { return maxc <= 16 ? 4 : 2; }
 constexpr int var_width(int maxv) { return maxv <= 8 ? 4 : maxv <= 16 ? 2 : 1; }
@@ -317,9 +378,11 @@ void pick_check(int dc, CheckFn& fn, int& w) {
 #undef QLDPC_E
 #undef QLDPC_B
 }
-void pick_var(int dv, VarFn& fn, int& w) {
-#define QLDPC_E(N) if (dv == N) { fn = g_var<N, var_width(N), true>; w = var_width(N); return; }
-#define QLDPC_B(N) if (dv <= N) { fn = g_var<N, var_width(N), false>; w = var_width(N); return; }
+void pick_var(int dv, VarFn& fn, VarFn& fn_last, int& w) {
+#define QLDPC_E(N) \
+  if (dv == N) { fn = g_var<N, var_width(N), true, false>; fn_last = g_var<N, var_width(N), true, true>; w = var_width(N); return; }
+#define QLDPC_B(N) \
+  if (dv <= N) { fn = g_var<N, var_width(N), false, false>; fn_last = g_var<N, var_width(N), false, true>; w = var_width(N); return; }
   QLDPC_B(1) QLDPC_E(2) QLDPC_E(3) QLDPC_E(4) QLDPC_E(5) QLDPC_E(6) QLDPC_E(7) QLDPC_E(8) QLDPC_E(9) QLDPC_E(10)
   QLDPC_E(11) QLDPC_E(12) QLDPC_B(16) QLDPC_B(32)
 #undef QLDPC_E
@@ -341,27 +404,30 @@ cudaError_t run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8
   s.bad = s.state + S;
   s.nanflag = s.bad + S;
   s.mismatch = s.nanflag + S;
+  s.decb = s.mismatch + S;
   s.frame = (int32_t*)a.words;
   s.iter = s.frame + S;
   s.ctr = (unsigned int*)(s.iter + S);
-  cudaMemsetAsync(dec, 0, (size_t)nframes * a.nw * sizeof(uint32_t), st);
-  const int sb = (S + 255) / 256, sx = (S + 127) / 128;
-  g_start<<<sb, 256, 0, st>>>(s, S);
+  s.lastflag = s.ctr + 4;
   CheckFn check = nullptr;
-  VarFn var = nullptr;
+  VarFn var = nullptr, var_last = nullptr;
   int wc = 1, wv = 1;
   pick_check(a.dc, check, wc);
-  pick_var(a.dv, var, wv);
-  const dim3 gc((S + 128 * wc - 1) / (128 * wc), m), gv((S + 128 * wv - 1) / (128 * wv), n), gd(sx, std::min(n, 32)), ge(sx, std::min(m, 32)), gf(sx, std::min(E, 64));
+  pick_var(a.dv, var, var_last, wv);
+  const int sb = (S + kGroup - 1) / kGroup, s1 = (S + 127) / 128, s4 = (S + 511) / 512;
+  const dim3 gc((S + 128 * wc - 1) / (128 * wc), m), gv((S + 128 * wv - 1) / (128 * wv), n);
+  const dim3 ge(s4, std::min(m, 32)), gp(s4, std::min(a.nw, 32)), gf(s1, std::min(m, 16));
   const int last_it = a.maxit - 1;
-  // A pass first hands frames to the slots that stopped in the previous pass (all of them before the first), then
-  // runs one BP iteration on every running slot.
+  g_start<<<sb, kGroup, 0, st>>>(s, S);
+  // A pass first serves the slots that stopped in the previous pass (before the first pass: all of them, with no
+  // frame to write out), then runs one BP iteration on every running slot.
   for (long long pass = 0;; ++pass) {
-    g_decide<<<gd, 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.nw, dec);
-    g_verify<<<ge, 128, 0, st>>>(s, a.cvar, m, a.dc, S, a.nw, dec);
-    g_handover<<<sb, 256, 0, st>>>(s, S, nframes, flags, iters);
-    g_fill<<<gf, 128, 0, st>>>(s, syn, a.mw, m, E, S, a.prior);
-    g_activate<<<sb, 256, 0, st>>>(s, S);
+    if (pass > 0) {
+      g_verify<<<ge, 128, 0, st>>>(s, a.cvar, m, a.dc, S);
+      g_pack<<<gp, 128, 0, st>>>(s, n, S, a.nw, dec);
+    }
+    g_handover<<<sb, kGroup, 0, st>>>(s, S, nframes, last_it, flags, iters);
+    g_fill<<<gf, 128, 0, st>>>(s, syn, a.mw, m, S);
     if (pass % 8 == 0) {  // completion is polled every few passes (a device-to-host copy and a stream sync)
       unsigned int completed = 0;
       cudaError_t e = cudaMemcpyAsync(&completed, s.ctr + 1, sizeof completed, cudaMemcpyDeviceToHost, st);
@@ -369,19 +435,20 @@ cudaError_t run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8
       if (e != cudaSuccess) return e;
       if (completed >= (unsigned)nframes) break;
     }
-    check<<<gc, 128, 0, st>>>(s, m, a.dc, S);
+    check<<<gc, 128, 0, st>>>(s, m, a.dc, S, a.prior);
     var<<<gv, 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.prior, last_it);
-    g_control<<<sb, 256, 0, st>>>(s, S, last_it);
+    if (pass >= last_it) var_last<<<gv, 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.prior, last_it);  // no slot is that old before
+    g_control<<<sb, kGroup, 0, st>>>(s, S, last_it);
   }
   return cudaGetLastError();
 }
 
 }  // namespace
 
-size_t global_bp_bytes(int m, int dc, int batch, size_t* msg_bytes, size_t* byte_bytes, size_t* word_bytes) {
+size_t global_bp_bytes(int m, int n, int dc, int batch, size_t* msg_bytes, size_t* byte_bytes, size_t* word_bytes) {
   *msg_bytes = (size_t)m * dc * batch * sizeof(float);
-  *byte_bytes = (size_t)m * batch + (size_t)4 * batch;
-  *word_bytes = ((size_t)2 * batch + 4) * sizeof(uint32_t);
+  *byte_bytes = ((size_t)m + 4 + n) * batch;
+  *word_bytes = ((size_t)2 * batch + 4 + (batch + 255) / 256) * sizeof(uint32_t);
   return *msg_bytes + *byte_bytes + *word_bytes;
 }
 

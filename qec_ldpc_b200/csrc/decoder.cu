@@ -226,7 +226,7 @@ int ensure_global(qldpc_decoder* d, int side) {
   batch = std::max<long long>(32, std::min<long long>(batch, ((long long)d->chunk + 31) / 32 * 32));
   s.gbatch = (int)std::min<long long>(batch, 1 << 16);
   size_t mb, bb, wb;
-  global_bp_bytes(s.m, s.dc, s.gbatch, &mb, &bb, &wb);
+  global_bp_bytes(s.m, n, s.dc, s.gbatch, &mb, &bb, &wb);
   CU_TRY(dev_alloc(s.gvrow, vrow.size()));
   CU_TRY(dev_alloc(s.gcvar, cvar.size()));
   CU_TRY(cudaMemcpy(s.gvrow, vrow.data(), vrow.size() * 4, cudaMemcpyHostToDevice));

@@ -31,10 +31,10 @@ struct GlobalBpArgs {
   const uint32_t* vrow;  // [dv][n]
   const uint32_t* cvar;  // [dc][m]
   float* msg;            // [E][batch]
-  uint8_t* bytes;        // syndrome bytes [m][batch] + 4 per-slot byte arrays
+  uint8_t* bytes;        // syndrome bytes [m][batch], 4 per-slot byte arrays, decision bytes [n][batch]
   uint32_t* words;       // frame ids [batch], iteration indices [batch], 2 counters
 };
-size_t global_bp_bytes(int m, int dc, int batch, size_t* msg_bytes, size_t* byte_bytes, size_t* word_bytes);
+size_t global_bp_bytes(int m, int n, int dc, int batch, size_t* msg_bytes, size_t* byte_bytes, size_t* word_bytes);
 cudaError_t global_bp_run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8_t* flags, uint32_t* iters,
                           int nframes, int* launches, cudaStream_t st);
 
