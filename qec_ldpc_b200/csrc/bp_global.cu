@@ -29,7 +29,7 @@ namespace {
 enum : uint8_t { kIdle = 0, kRun = 1, kDone = 2, kFresh = 3 };
 __device__ __forceinline__ bool running(uint8_t st) { return st == kRun || st == kFresh; }
 
-constexpr int kGroup = 256;  // slots per control block = granularity of the `lastflag` hints
+constexpr int kGroup = 256;  // slots per control block
 
 struct Slots {
   float* msg;          // [E][S]
@@ -41,8 +41,8 @@ struct Slots {
   uint8_t* decb;       // [n][S] hard decision after the last checkpoint variable phase, one byte per bit
   int32_t* frame;      // [S] frame id in the slot
   int32_t* iter;       // [S] iteration index n of the slot
-  unsigned int* ctr;   // [0] next frame to hand out, [1] frames completed
-  uint32_t* lastflag;  // [ceil(S / kGroup)] some slot of the group is in its last iteration in the coming pass
+  unsigned int* ctr;   // [0] next frame to hand out, [1] frames completed, [2], [3] lengths of the two `lastq` lists
+  uint32_t* lastq;     // [2][S] thread indices (slot / W) of the variable kernel with a slot entering its last iteration
 };
 
 // Every slot starts "stopped" with no frame to write out: g_handover gives it its first frame.
@@ -54,8 +54,7 @@ __global__ void __launch_bounds__(kGroup) g_start(Slots s, int S) {
     s.iter[t] = 0;
     s.bad[t] = s.nanflag[t] = s.mismatch[t] = 0;
   }
-  if (threadIdx.x == 0) s.lastflag[blockIdx.x] = 0;
-  if (t < 2) s.ctr[t] = 0;
+  if (t < 4) s.ctr[t] = 0;
 }
 
 // W consecutive slots per thread, moved with one 4*W-byte access per message row: a pass is bound by HBM, and wide
@@ -153,19 +152,20 @@ __global__ void __launch_bounds__(128) g_check(Slots s, int m, int dc_rt, int S,
 }
 
 // Two launches per pass: LAST = false serves the threads none of whose slots is in its final iteration (no
-// full-product registers: higher occupancy for a bandwidth-bound kernel), LAST = true the others (DecoderCPU.h:284);
-// the latter first consults the per-group hints g_control left and normally retires at once.
+// full-product registers: higher occupancy for a bandwidth-bound kernel), LAST = true the others (DecoderCPU.h:284).
+// The latter works from the list g_control compiled in the previous pass (`lastq`, usually empty or short), or
+// over all threads if `lastq` is null (one-iteration runs, where every slot is in its last iteration).
 template <int MAXV, int W, bool EXACT, bool LAST>
 __global__ void __launch_bounds__(128) g_var(Slots s, const uint32_t* __restrict__ vrow, int n, int dv_rt, int S,
-                                             float prior, int last_it) {
+                                             float prior, int last_it, const uint32_t* __restrict__ lastq,
+                                             const unsigned int* __restrict__ lastq_len) {
   const int dv = EXACT ? MAXV : dv_rt;
-  if (LAST) {
-    const int lo = blockIdx.x * (128 * W) / kGroup, hi = min((S - 1) / kGroup, ((blockIdx.x + 1) * (128 * W) - 1) / kGroup);
-    uint32_t hint = 0;
-    for (int g = lo; g <= hi; ++g) hint |= s.lastflag[g];
-    if (!hint) return;
+  int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (LAST && lastq) {
+    if (t >= (int)*lastq_len) return;
+    t = (int)lastq[t];
   }
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) * W;
+  const int f = t * W;
   const int v = blockIdx.y;
   if (f >= S) return;
   uint8_t st[W];
@@ -261,9 +261,10 @@ __global__ void __launch_bounds__(128) g_var(Slots s, const uint32_t* __restrict
 }
 
 // BeliefPropogation loop control (DecoderCPU.h:280-291), per slot, after the variable phase.
-__global__ void __launch_bounds__(kGroup) g_control(Slots s, int S, int last_it) {
+__global__ void __launch_bounds__(kGroup) g_control(Slots s, int S, int last_it, int wv, int parity) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  int next_is_last = 0;
+  if (f == 0) s.ctr[2 + (parity ^ 1)] = 0;  // the list the next pass's g_control appends to; its reader has run
+  bool next_is_last = false;
   if (f < S && running(s.state[f])) {
     const int it = s.iter[f];
     const bool last = it == last_it, ck = last || it % 10 == 0;
@@ -276,8 +277,12 @@ __global__ void __launch_bounds__(kGroup) g_control(Slots s, int S, int last_it)
       next_is_last = it + 1 == last_it;
     }
   }
-  next_is_last = __syncthreads_or(next_is_last);
-  if (threadIdx.x == 0) s.lastflag[blockIdx.x] = next_is_last;
+  // one list entry per variable-kernel thread (wv consecutive slots): the lowest flagged slot of the group appends
+  const unsigned flagged = __ballot_sync(0xffffffffu, next_is_last);
+  const int lane = threadIdx.x & 31, first = lane & ~(wv - 1);
+  const unsigned group = (flagged >> first) & ((1u << wv) - 1u);
+  if (next_is_last && (group & ((1u << (lane - first)) - 1u)) == 0)
+    s.lastq[(size_t)parity * S + atomicAdd(&s.ctr[2 + parity], 1u)] = (uint32_t)(f / wv);
 }
 
 // syndrome of the decision against the input syndrome (DecoderCPU.h:380-384), for the slots that just stopped
@@ -330,7 +335,7 @@ __global__ void __launch_bounds__(128) g_pack(Slots s, int n, int S, int nw, uin
 }
 
 // per-frame outputs of the stopped slots, then the hand-over to the next frame of the queue
-__global__ void __launch_bounds__(kGroup) g_handover(Slots s, int S, int nframes, int last_it, uint8_t* __restrict__ flags,
+__global__ void __launch_bounds__(kGroup) g_handover(Slots s, int S, int nframes, uint8_t* __restrict__ flags,
                                                      uint32_t* __restrict__ iters) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
   if (f >= S || s.state[f] != kDone) return;
@@ -347,7 +352,6 @@ __global__ void __launch_bounds__(kGroup) g_handover(Slots s, int S, int nframes
   if (next < (unsigned)nframes) {
     s.frame[f] = (int)next;
     s.state[f] = kFresh;
-    if (last_it == 0) s.lastflag[blockIdx.x] = 1;  // a one-iteration run: the first iteration is the last
   } else {
     s.frame[f] = -1;
     s.state[f] = kIdle;
@@ -364,7 +368,7 @@ __global__ void __launch_bounds__(128) g_fill(Slots s, const uint32_t* __restric
 }
 
 using CheckFn = void (*)(Slots, int, int, int, float);
-using VarFn = void (*)(Slots, const uint32_t*, int, int, int, float, int);
+using VarFn = void (*)(Slots, const uint32_t*, int, int, int, float, int, const uint32_t*, const unsigned int*);
 constexpr int check_width(int maxc) { return maxc <= 16 ? 4 : 2; }
 constexpr int var_width(int maxv) { return maxv <= 8 ? 4 : maxv <= 16 ? 2 : 1; }
 
@@ -408,7 +412,7 @@ cudaError_t run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8
   s.frame = (int32_t*)a.words;
   s.iter = s.frame + S;
   s.ctr = (unsigned int*)(s.iter + S);
-  s.lastflag = s.ctr + 4;
+  s.lastq = s.ctr + 4;
   CheckFn check = nullptr;
   VarFn var = nullptr, var_last = nullptr;
   int wc = 1, wv = 1;
@@ -426,7 +430,7 @@ cudaError_t run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8
       g_verify<<<ge, 128, 0, st>>>(s, a.cvar, m, a.dc, S);
       g_pack<<<gp, 128, 0, st>>>(s, n, S, a.nw, dec);
     }
-    g_handover<<<sb, kGroup, 0, st>>>(s, S, nframes, last_it, flags, iters);
+    g_handover<<<sb, kGroup, 0, st>>>(s, S, nframes, flags, iters);
     g_fill<<<gf, 128, 0, st>>>(s, syn, a.mw, m, S);
     if (pass % 8 == 0) {  // completion is polled every few passes (a device-to-host copy and a stream sync)
       unsigned int completed = 0;
@@ -436,9 +440,14 @@ cudaError_t run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8
       if (completed >= (unsigned)nframes) break;
     }
     check<<<gc, 128, 0, st>>>(s, m, a.dc, S, a.prior);
-    var<<<gv, 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.prior, last_it);
-    if (pass >= last_it) var_last<<<gv, 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.prior, last_it);  // no slot is that old before
-    g_control<<<sb, kGroup, 0, st>>>(s, S, last_it);
+    const int parity = (int)(pass & 1);
+    var<<<gv, 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.prior, last_it, nullptr, nullptr);
+    if (last_it == 0)
+      var_last<<<gv, 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.prior, last_it, nullptr, nullptr);
+    else if (pass >= last_it)  // no slot is that old before; the list was written by the previous pass's g_control
+      var_last<<<gv, 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.prior, last_it, s.lastq + (size_t)(parity ^ 1) * S,
+                                   s.ctr + 2 + (parity ^ 1));
+    g_control<<<sb, kGroup, 0, st>>>(s, S, last_it, wv, parity);
   }
   return cudaGetLastError();
 }
@@ -448,7 +457,7 @@ cudaError_t run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8
 size_t global_bp_bytes(int m, int n, int dc, int batch, size_t* msg_bytes, size_t* byte_bytes, size_t* word_bytes) {
   *msg_bytes = (size_t)m * dc * batch * sizeof(float);
   *byte_bytes = ((size_t)m + 4 + n) * batch;
-  *word_bytes = ((size_t)2 * batch + 4 + (batch + 255) / 256) * sizeof(uint32_t);
+  *word_bytes = ((size_t)4 * batch + 4) * sizeof(uint32_t);
   return *msg_bytes + *byte_bytes + *word_bytes;
 }
 
