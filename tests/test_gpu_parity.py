@@ -341,3 +341,23 @@ def test_shapes_without_tile_kernel_use_global_path(qldpc, oracle, prm, maxit):
         a = dec.get_statistics_depolarizing(5, 0, 2500, 0.04, maxit, per_frame=True)
         assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
         assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))
+
+
+def test_code_too_large_for_shared_memory_uses_global_path(qldpc, oracle):
+    """A frame-side of 59936 edges (240 KB of messages) does not fit the tile kernel: the decoder falls back to the
+    HBM-resident path on its own and still matches the oracle frame for frame."""
+    prm = (4, 4, 8, 1873, 737, 2)
+    gc = qldpc.Code.qc(*prm)
+    dec = qldpc.Decoder(gc, 0, 256)
+    assert dec.launch_info(0)["vec"] == -1 and dec.launch_info(1)["vec"] == -1
+    with pytest.raises(qldpc.QldpcError):
+        dec.configure(0, 1, 0, 0)  # an explicit tile shape that cannot fit is refused, not silently replaced
+    oc = oracle.code_qc(*prm)
+    oc.set_logical(gc.dense_matrix(2))
+    b = oc.run_depolarizing(31, 0, 48, 0.03, 30)
+    for slots in (0, 32):
+        for side in (0, 1):
+            dec.configure(side, -1, slots, 0)
+        a = dec.get_statistics_depolarizing(31, 0, 48, 0.03, 30, per_frame=True)
+        assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
+        assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))
