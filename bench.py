@@ -308,6 +308,15 @@ def run_native(args):
             smem_peak = float(json.load(open(spath))["roofline_denominator_gbs"])
             smem_src = "measured (profiles/smem_peak.json, tools/micro/smem_bw.cu); nominal %.0f GB/s" % smem_nominal
         step_kernel_ms = sum(kms.values())
+
+        def fp32_ops(dc, dv):  # FP32 instructions x lanes per edge-update of the reference's arithmetic
+            check = dc * (dc - 1) / 2.0 + (dc - 2) + 2 * dc          # exclusive products with shared prefix, 1-2q, r
+            var = dv * (dv - 1) + 2 * (dv - 1) + dv + dv + 5 * dv    # P and Q chains, prefixes, 1-p, Q+P, division
+            return check / dc + var / dv
+        fp32_total = (int(counters[9]) * code.EX * fp32_ops(code.dcX, code.dvX)
+                      + int(counters[10]) * code.EZ * fp32_ops(code.dcZ, code.dvZ))
+        fp32_achieved = fp32_total / (bp_ms * 1e-3) / 1e9
+        fp32_peak = 148 * 128 * sm_mhz * 1e6 / 1e9
         line = {
             "metric": METRIC, "value": value, "unit": "frames/s", "n_gpus": n_gpus, "steps": args.steps,
             "warmup": args.warmup, "ms_per_step": ms_total / args.steps, "higher_is_better": True, "scaling": "weak",
@@ -327,6 +336,10 @@ def run_native(args):
             "smem_roofline": {"bound": "smem", "achieved": achieved, "peak": smem_peak, "unit": "GB/s",
                               "frac": achieved / smem_peak,
                               "peak_source": smem_src},
+            "fp32_roofline": {"bound": "fp32 pipe", "achieved": fp32_achieved, "peak": fp32_peak,
+                              "unit": "G lane-instructions/s (an FMA counts once)", "frac": fp32_achieved / fp32_peak,
+                              "peak_source": "148 SM x 128 FP32 lanes x %.0f MHz (sampled under load)" % sm_mhz,
+                              "note": "operation count fixed by the reference's arithmetic order (bit-exact parity)"},
             "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
             "launch": {"x": info[0], "z": info[1]},
             "e2e": {"value": F * n_gpus * args.steps / e2e_s, "unit": "frames/s",

@@ -209,6 +209,8 @@ class Decoder:
         _check(self._lib.qldpc_decoder_set_stream(self.h, C.c_void_p(stream_ptr)))
 
     def configure(self, side, frames_per_tile=0, threads=0, ctas_per_sm=0):
+        """Launch shape of one side (0 = heuristic).  frames_per_tile=-1 forces the HBM-resident path; `threads` is
+        then the number of frame slots kept in flight."""
         _check(self._lib.qldpc_decoder_configure(self.h, side, frames_per_tile, threads, ctas_per_sm))
 
     def launch_info(self, side):
