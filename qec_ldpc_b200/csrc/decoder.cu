@@ -765,6 +765,7 @@ int qldpc_get_statistics_depolarizing(qldpc_decoder* dec, uint64_t seed, uint64_
   int rc = check_common(dec, nframes, maxIterations);
   if (rc) return rc;
   qldpc_decoder* d = dec;
+  if (p != p) return fail(QLDPC_ERR_ARG, "error probability is NaN");
   const Thresholds thr = depolarizing_thresholds(p);
   CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
   for (int64_t off = 0; off < nframes; off += d->chunk) {
@@ -899,6 +900,7 @@ int qldpc_debug_generate(qldpc_decoder* dec, uint64_t seed, uint64_t first_frame
   const size_t per = (size_t)std::max(n, std::max(mX, mZ));
   rc = ensure_stage(d, per * std::min<int64_t>(d->chunk, std::max<int64_t>(nframes, 1)));
   if (rc) return rc;
+  if (p != p) return fail(QLDPC_ERR_ARG, "error probability is NaN");
   const Thresholds thr = depolarizing_thresholds(p);
   for (int64_t off = 0; off < nframes; off += d->chunk) {
     const int nf = (int)std::min<int64_t>(d->chunk, nframes - off);

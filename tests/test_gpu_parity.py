@@ -361,3 +361,19 @@ def test_code_too_large_for_shared_memory_uses_global_path(qldpc, oracle):
         a = dec.get_statistics_depolarizing(31, 0, 48, 0.03, 30, per_frame=True)
         assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
         assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))
+
+
+def test_argument_errors_are_reported(qldpc, decoders):
+    """Bad arguments come back as error codes (QldpcError here), never as a crash or a silent result."""
+    gc, dec = decoders("C1")
+    with pytest.raises(qldpc.QldpcError):
+        dec.get_statistics_depolarizing(1, 0, 10, 0.05, 0)  # no iterations
+    with pytest.raises(qldpc.QldpcError):
+        dec.get_statistics_depolarizing(1, 0, -1, 0.05, 20)  # negative frame count
+    with pytest.raises(qldpc.QldpcError):
+        dec.get_statistics_depolarizing(1, 0, 10, float("nan"), 20)
+    with pytest.raises(qldpc.QldpcError):
+        dec.configure(2, 0, 0, 0)  # no such side
+    with pytest.raises(qldpc.QldpcError):
+        dec.configure(0, 3, 0, 0)  # no 3-slot tile
+    assert int(dec.get_statistics_depolarizing(1, 0, 10, 0.05, 20)["counters"][0]) == 10  # still usable afterwards
