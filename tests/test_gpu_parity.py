@@ -308,7 +308,9 @@ def test_global_memory_path_matches_oracle(qldpc, oracle, code, nf):
     assert np.array_equal(dec.get_statistics_depolarizing(77, 3, nf, p, maxit)["counters"], b["counters"])
 
 
-@pytest.mark.parametrize("prm,shapes", [((3, 4, 8, 13, 5, 2), ((8, 3), (8, 4))), ((6, 6, 12, 7, 3, 2), ((12, 6), (12, 6)))])
+@pytest.mark.parametrize("prm,shapes", [((3, 4, 8, 13, 5, 2), ((8, 3), (8, 4))), ((6, 6, 12, 7, 3, 2), ((12, 6), (12, 6))),
+                                        ((3, 4, 10, 31, 2, 2), ((10, 3), (10, 4))), ((3, 4, 12, 13, 4, 2), ((12, 3), (12, 4))),
+                                        ((5, 6, 12, 37, 11, 2), ((12, 5), (12, 6)))])
 def test_other_instantiated_shapes(qldpc, oracle, prm, shapes):
     """The remaining compiled (check degree, variable degree) instantiations of the tile kernel, all tile widths."""
     gc = qldpc.Code.qc(*prm)
