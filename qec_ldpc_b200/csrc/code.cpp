@@ -3,11 +3,13 @@
 #include "code.h"
 
 #include <algorithm>
+#include <atomic>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
 #include <fstream>
 #include <sstream>
+#include <thread>
 
 namespace qldpc {
 
@@ -15,26 +17,91 @@ namespace qldpc {
 // GF(2) helpers
 // ---------------------------------------------------------------------------------------------------
 
-// Gauss-Jordan elimination; keeps only the non-zero (basis) rows, in order of their pivot column.
+// Gauss-Jordan elimination; keeps only the non-zero (basis) rows, in order of their pivot column.  Matrices of
+// big codes (n ~ 10^4: 10^10..10^11 word operations) are eliminated by a few threads, each owning a block of rows;
+// the result does not depend on the thread count (rows are independent once the pivot row is fixed).
+namespace {
+struct SpinBarrier {
+  explicit SpinBarrier(int n) : count(n) {}
+  void wait() {
+    const int gen = generation.load(std::memory_order_acquire);
+    if (arrived.fetch_add(1, std::memory_order_acq_rel) + 1 == count) {
+      arrived.store(0, std::memory_order_relaxed);
+      generation.store(gen + 1, std::memory_order_release);
+    } else {
+      int spins = 0;
+      while (generation.load(std::memory_order_acquire) == gen)
+        if (++spins > 4096) std::this_thread::yield();
+    }
+  }
+  const int count;
+  std::atomic<int> arrived{0}, generation{0};
+};
+}  // namespace
+
 static int rref(BitMatrix& a, std::vector<int>* pivots) {
-  int rank = 0;
   const int W = a.words;
-  for (int col = 0; col < a.cols && rank < a.rows; ++col) {
-    const int wi = col >> 5;
-    const uint32_t bit = 1u << (col & 31);
-    int piv = -1;
-    for (int r = rank; r < a.rows; ++r)
-      if (a.w[(size_t)r * W + wi] & bit) { piv = r; break; }
-    if (piv < 0) continue;
-    if (piv != rank) std::swap_ranges(a.row(piv), a.row(piv) + W, a.row(rank));
-    const uint32_t* p = a.row(rank);
-    for (int r = 0; r < a.rows; ++r)
-      if (r != rank && (a.w[(size_t)r * W + wi] & bit)) {
-        uint32_t* q = a.row(r);
-        for (int k = 0; k < W; ++k) q[k] ^= p[k];
+  const double work = (double)a.rows * a.rows * W;
+  int nthreads = 1;
+  if (work > 2e10) nthreads = (int)std::max(1u, std::min(16u, std::thread::hardware_concurrency()));
+  if (const char* env = std::getenv("QLDPC_HOST_THREADS")) nthreads = std::max(1, std::min(64, std::atoi(env)));
+  nthreads = std::min(nthreads, std::max(1, a.rows));
+  int rank = 0, col = 0, k0 = 0, wi = 0;
+  uint32_t bit = 0;
+  bool done = false;
+  // picks the next pivot (serial part): leaves col / wi / bit / k0 describing it, or done = true
+  auto next_pivot = [&]() {
+    for (; col < a.cols && rank < a.rows; ++col) {
+      wi = col >> 5;
+      bit = 1u << (col & 31);
+      int piv = -1;
+      for (int r = rank; r < a.rows; ++r)
+        if (a.w[(size_t)r * W + wi] & bit) { piv = r; break; }
+      if (piv < 0) continue;
+      if (piv != rank) std::swap_ranges(a.row(piv), a.row(piv) + W, a.row(rank));
+      const uint32_t* p = a.row(rank);
+      k0 = 0;  // the pivot row is zero in every earlier pivot column: usually its leading words are all zero
+      while (k0 < wi && p[k0] == 0) ++k0;
+      if (pivots) pivots->push_back(col);
+      return;
+    }
+    done = true;
+  };
+  auto eliminate = [&](int r0, int r1) {
+    // locals, so that the inner loop vectorises (the captured variables could alias the words being written)
+    const int pivot_row = rank, first = k0, word = wi, len = W - k0;
+    const uint32_t mask = bit;
+    const uint32_t* __restrict p = a.row(pivot_row) + first;
+    uint32_t* base = a.w.data();
+    for (int r = r0; r < r1; ++r)
+      if (r != pivot_row && (base[(size_t)r * W + word] & mask)) {
+        uint32_t* __restrict q = base + (size_t)r * W + first;
+        for (int k = 0; k < len; ++k) q[k] ^= p[k];
       }
-    if (pivots) pivots->push_back(col);
-    ++rank;
+  };
+  if (nthreads == 1) {
+    for (next_pivot(); !done; next_pivot()) {
+      eliminate(0, a.rows);
+      ++rank;
+      ++col;
+    }
+  } else {
+    SpinBarrier barrier(nthreads);
+    auto worker = [&](int t) {
+      const int r0 = (int)((long long)a.rows * t / nthreads), r1 = (int)((long long)a.rows * (t + 1) / nthreads);
+      for (;;) {
+        if (t == 0) next_pivot();
+        barrier.wait();  // pivot published
+        if (done) return;
+        eliminate(r0, r1);
+        barrier.wait();  // all rows updated before the next pivot search reads them
+        if (t == 0) { ++rank; ++col; }
+      }
+    };
+    std::vector<std::thread> pool;
+    for (int t = 1; t < nthreads; ++t) pool.emplace_back(worker, t);
+    worker(0);
+    for (auto& th : pool) th.join();
   }
   a.rows = rank;
   a.w.resize((size_t)rank * W);
@@ -187,6 +254,10 @@ static void classify_logical(Code& c, BitMatrix& rows) {
 static void generate_logical(Code& c) {
   BitMatrix nx = null_space(pcm_bits(c.side[0], c.n));
   BitMatrix nz = null_space(pcm_bits(c.side[1], c.n));
+  // The stacked matrix [nx 0; 0 nz] is block diagonal, so its reduced form is the two reduced blocks stacked
+  // (x pivots come first); reducing them separately works on rows of half the width.
+  row_reduce(nx);
+  row_reduce(nz);
   BitMatrix rows(nx.rows + nz.rows, 2 * c.n);
   for (int r = 0; r < nx.rows; ++r)
     for (int col = 0; col < c.n; ++col)
@@ -194,7 +265,6 @@ static void generate_logical(Code& c) {
   for (int r = 0; r < nz.rows; ++r)
     for (int col = 0; col < c.n; ++col)
       if (nz.get(r, col)) rows.set(nx.rows + r, c.n + col);
-  row_reduce(rows);
   classify_logical(c, rows);
   c.logical_from_file = false;
 }
