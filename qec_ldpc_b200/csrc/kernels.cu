@@ -65,7 +65,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
       if (sm_bytes > smem_optin) continue;
       const int smem_ctas = std::max(1, smem_sm / (sm_bytes + 1024));
       const int regs_v = (regs_of(v) + 7) / 8 * 8;
-      for (int w = 2; w <= kMaxT / 32; ++w) {
+      for (int w = 1; w <= kMaxT / 32; ++w) {
         if (threads != 0 && 32 * w != threads) continue;
         const int reg_ctas = 65536 / (regs_v * 32 * w);
         if (reg_ctas < 1) continue;
@@ -75,7 +75,9 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
         // A CTA whose warp count is not a multiple of 4 loads one SM sub-partition with two of its warps; since the
         // packed-FP32 kernel keeps the FMA pipe ~2/3 busy, that sub-partition then paces every phase of the CTA
         // (measured on the Z side of J4K5L10P61: 4 warps 9.85e11 vs 5 warps 9.33e11 edge-updates/s).
-        const double balance = w % 4 == 0 ? 1.0 : 0.92;
+        // Single-warp CTAs (tiny codes: one warp covers a whole phase) are spread over the sub-partitions by the CTA
+        // scheduler instead (measured on J3K3L6P7: 1 warp 6.9e11 vs 2 warps 4.6e11 edge-updates/s).
+        const double balance = w % 4 == 0 || w == 1 ? 1.0 : 0.92;
         // beyond 16 warps extra residency still buys a few per cent (measured: 28 warps of the 2-slot tile beat 20 warps
         // of the 4-slot tile by 2-4%), which outweighs the wider tile's saving in shared-memory instructions
         // (tiles of 2 or 4 slots use the packed fp32x2 arithmetic, the 1-slot tile cannot)

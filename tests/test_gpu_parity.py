@@ -198,7 +198,7 @@ def test_tile_width_and_launch_shape_do_not_change_results(qldpc):
     gc = qldpc.Code.qc(*CODES["C2"])
     dec = qldpc.Decoder(gc, 0, 1 << 14)
     ref = None
-    for vec, threads in [(4, 0), (2, 0), (1, 0), (4, 64), (4, 256), (2, 96)]:
+    for vec, threads in [(4, 0), (2, 0), (1, 0), (4, 64), (4, 256), (2, 96), (2, 32), (1, 32)]:
         for side in (0, 1):
             dec.configure(side, vec, threads, 0)
         a = dec.get_statistics_depolarizing(8, 0, 5000, 0.06, 50, per_frame=True)

@@ -12,7 +12,7 @@ dec.enable_timing(True)
 best = {}
 for side in (0, 1):
     for vec in (4, 2, 1):
-        for thr in (64, 96, 128, 160, 192, 224, 256, 384, 512):
+        for thr in (32, 64, 96, 128, 160, 192, 224, 256, 384, 512):
             try:
                 dec.configure(side, vec, thr, 0)
             except q.QldpcError:
