@@ -238,6 +238,7 @@ def run_native(args):
     # DecoderGPU::GetStats(..., xErrors, zErrors) (DecoderGPU.h:193): pre-generated patterns in host memory, in the
     # reference's layout (one int per qubit, frame-major); H2D copies, decode and the D2H counter read are timed.
     n = code.n
+    code_nw = (n + 31) // 32
     xh = torch.empty((F, n), dtype=torch.int32, pin_memory=True)
     zh = torch.empty((F, n), dtype=torch.int32, pin_memory=True)
     sl = 100_000
@@ -246,16 +247,31 @@ def run_native(args):
         x, z, _, _ = dec.debug_generate(SEED, first_frame(0) + off, cnt, P)
         xh[off:off + cnt] = torch.from_numpy(x)
         zh[off:off + cnt] = torch.from_numpy(z)
-    e2e_counters = None
-    for s in range(max(1, min(args.warmup, 2))):
-        dec.get_stats_from_errors_ptr(xh.data_ptr(), zh.data_ptr(), F, P, MAXIT, elem=4)
-    barrier()
-    t0 = time.perf_counter()
-    for s in range(args.steps):
-        e2e_counters = dec.get_stats_from_errors_ptr(xh.data_ptr(), zh.data_ptr(), F, P, MAXIT, elem=4)
-    torch.cuda.synchronize()
-    e2e_s = time.perf_counter() - t0
-    e2e_s = allreduce_max(e2e_s, "cuda")
+    # The library packs the rows to bits with host threads before the copy (1/32 of the bytes cross the link); with
+    # many ranks per box there are too few cores per rank for that, and it copies the raw rows instead (threads = 0).
+    local_world = int(os.environ.get("LOCAL_WORLD_SIZE", n_gpus))
+    host_threads = min(16, len(os.sched_getaffinity(0)) // max(1, local_world))
+    if host_threads < 6:
+        host_threads = 0
+
+    def time_i32(threads):
+        dec.set_host_threads(threads)
+        out = None
+        for s in range(max(1, min(args.warmup, 2))):
+            dec.get_stats_from_errors_ptr(xh.data_ptr(), zh.data_ptr(), F, P, MAXIT, elem=4)
+        barrier()
+        t0 = time.perf_counter()
+        for s in range(args.steps):
+            out = dec.get_stats_from_errors_ptr(xh.data_ptr(), zh.data_ptr(), F, P, MAXIT, elem=4)
+        torch.cuda.synchronize()
+        return allreduce_max(time.perf_counter() - t0, "cuda"), out
+
+    e2e_raw_s, e2e_counters = time_i32(0)
+    if host_threads > 0:
+        e2e_s, packed_counters = time_i32(host_threads)
+        assert np.array_equal(packed_counters, e2e_counters)
+    else:
+        e2e_s = e2e_raw_s
     # same patterns as step 0 of the device-resident run => same counters (checked on every rank)
     chk = dec.get_statistics_depolarizing(SEED, first_frame(0), F, P, MAXIT)["counters"]
     assert np.array_equal(chk, e2e_counters), "host-buffer path and device-generated path disagree"
@@ -343,14 +359,21 @@ def run_native(args):
             "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
             "launch": {"x": info[0], "z": info[1]},
             "e2e": {"value": F * n_gpus * args.steps / e2e_s, "unit": "frames/s",
-                    "h2d_bytes_per_step": 2 * F * n * 4, "d2h_bytes_per_step": q.NUM_COUNTERS * 8,
+                    "h2d_bytes_per_step": 2 * F * (code_nw * 4 if host_threads > 0 else n * 4),
+                    "d2h_bytes_per_step": q.NUM_COUNTERS * 8,
+                    "host_buffer_bytes_per_step": 2 * F * n * 4, "host_threads": host_threads,
                     "api": "qldpc_get_stats_from_errors_i32 (DecoderGPU::GetStats layout, pinned host int32)",
-                    "note": "the reference's layout spends one int32 per qubit (4880 B per frame): this number is "
-                            "bound by the H2D link (about 51 GB/s per GPU, about 200 GB/s of host memory traffic per "
-                            "box), not by the decoder; u8_patterns and device_generated show the other two entry points",
+                    "note": "the reference's layout spends one int32 per qubit (4880 B per frame); the library's host "
+                            "threads pack the rows to bits before the copy (host_threads > 0), otherwise the raw rows "
+                            "cross the link (raw_rows_over_link: bound by the H2D link, about 51 GB/s per GPU); "
+                            "u8_patterns and device_generated show the other two entry points",
                     "ms_per_step": 1e3 * e2e_s / args.steps,
+                    "raw_rows_over_link": {"value": F * n_gpus * args.steps / e2e_raw_s, "unit": "frames/s",
+                                           "h2d_bytes_per_step": 2 * F * n * 4, "host_threads": 0},
                     "u8_patterns": {"value": F * n_gpus * args.steps / e2e_u8_s, "unit": "frames/s",
-                                    "h2d_bytes_per_step": 2 * F * n, "api": "qldpc_get_stats_from_errors_u8"},
+                                    "h2d_bytes_per_step": 2 * F * (code_nw * 4 if host_threads > 0 else n),
+                                    "host_buffer_bytes_per_step": 2 * F * n, "host_threads": host_threads,
+                                    "api": "qldpc_get_stats_from_errors_u8"},
                     "device_generated": {"value": F * n_gpus * args.steps / e2e_gs_s, "unit": "frames/s",
                                          "h2d_bytes_per_step": 0, "d2h_bytes_per_step": q.NUM_COUNTERS * 8,
                                          "api": "qldpc_get_statistics_depolarizing (host wall clock)"}},

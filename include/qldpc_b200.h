@@ -120,6 +120,12 @@ int qldpc_decoder_set_stream(qldpc_decoder* dec, void* cuda_stream);
  * shared-memory tile kernel does not cover (no instantiation for the degrees, or a frame larger than shared memory);
  * with -1, threads_per_cta is the number of frame slots kept in flight (0 = heuristic) and ctas_per_sm is ignored. */
 int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, int threads_per_cta, int ctas_per_sm);
+/* Host-buffer entry points (qldpc_get_stats_from_errors_*, qldpc_decode_batch) convert the reference's
+ * one-element-per-bit rows to packed words on the host with `threads` worker threads, so that 1/32 (int) or 1/8 (byte)
+ * of the bytes cross the host-device link.  threads < 0: default (environment QLDPC_HOST_THREADS, else
+ * min(16, hardware threads)); 0: off -- raw rows are copied and packed on the device (use this when many ranks share
+ * few host cores).  Marshalling only: the decode itself never runs on the host. */
+int qldpc_decoder_set_host_threads(qldpc_decoder* dec, int threads);
 /* Launch geometry in use: out[0..7] = vec (-1: global-memory path), threads, ctas_per_sm, grid, dyn_smem_bytes, regs,
  * SM count, frames per launch. */
 int qldpc_decoder_launch_info(qldpc_decoder* dec, int side, int32_t out[8]);
@@ -183,6 +189,10 @@ int qldpc_decoder_get_timing(qldpc_decoder* dec, double* ms, uint64_t* launches,
 
 /* ---- parity taps (tests) ------------------------------------------------------------------------------- */
 
+/* Test taps for the host-side marshalling (host_pack.h); they run without a GPU.  pack: dst[r][w] bit b =
+ * (src[r][32 w + b] != 0), rows of ceil(cols/32) words; unpack: the inverse, one byte per bit. */
+int qldpc_debug_host_pack(const void* src, int elem_size, int64_t rows, int cols, uint32_t* dst, int threads);
+int qldpc_debug_host_unpack(const uint32_t* src, int64_t rows, int cols, uint8_t* dst, int threads);
 /* Device Philox generator + syndrome kernel, unpacked to host bytes: xerr, zerr [nframes x n],
  * synX [nframes x mX], synZ [nframes x mZ] (any may be NULL). */
 int qldpc_debug_generate(qldpc_decoder* dec, uint64_t seed, uint64_t first_frame, int64_t nframes, float p,

@@ -69,6 +69,7 @@ def load_library():
     L.qldpc_decoder_destroy.restype = None
     L.qldpc_decoder_set_stream.argtypes = [vp, vp]
     L.qldpc_decoder_configure.argtypes = [vp, i32, i32, i32, i32]
+    L.qldpc_decoder_set_host_threads.argtypes = [vp, i32]
     L.qldpc_decoder_launch_info.argtypes = [vp, i32, vp]
     L.qldpc_decode_batch.argtypes = [vp, vp, vp, i64, f32, i32, vp, vp, vp, vp]
     L.qldpc_decode_batch_device.argtypes = [vp, vp, vp, i64, f32, i32, vp, vp, vp, vp]
@@ -79,6 +80,8 @@ def load_library():
     L.qldpc_decoder_enable_timing.argtypes = [vp, i32]
     L.qldpc_decoder_get_timing.argtypes = [vp, vp, vp, i32]
     L.qldpc_debug_division_check.argtypes = [vp, u64, i64, vp]
+    L.qldpc_debug_host_pack.argtypes = [vp, i32, i64, i32, vp, i32]
+    L.qldpc_debug_host_unpack.argtypes = [vp, i64, i32, vp, i32]
     L.qldpc_debug_generate.argtypes = [vp, u64, u64, i64, f32, vp, vp, vp, vp]
     L.qldpc_debug_bp_trace.argtypes = [vp, i32, vp, i32, f32, i32, i32, vp, vp, vp]
     _lib = L
@@ -93,6 +96,22 @@ def _check(rc):
 
 def _ptr(a):
     return None if a is None else a.ctypes.data_as(C.c_void_p)
+
+
+def host_pack(rows, threads=4):
+    """Test tap: bit-packs a 2-D uint8 / int32 array row by row with the library's host packer."""
+    a = np.ascontiguousarray(rows)
+    assert a.ndim == 2 and a.dtype in (np.uint8, np.int32)
+    out = np.zeros((a.shape[0], (a.shape[1] + 31) // 32), np.uint32)
+    _check(load_library().qldpc_debug_host_pack(_ptr(a), a.dtype.itemsize, a.shape[0], a.shape[1], _ptr(out), threads))
+    return out
+
+
+def host_unpack(words, cols, threads=4):
+    w = np.ascontiguousarray(words, np.uint32)
+    out = np.zeros((w.shape[0], cols), np.uint8)
+    _check(load_library().qldpc_debug_host_unpack(_ptr(w), w.shape[0], cols, _ptr(out), threads))
+    return out
 
 
 class Code:
@@ -212,6 +231,10 @@ class Decoder:
         """Launch shape of one side (0 = heuristic).  frames_per_tile=-1 forces the HBM-resident path; `threads` is
         then the number of frame slots kept in flight."""
         _check(self._lib.qldpc_decoder_configure(self.h, side, frames_per_tile, threads, ctas_per_sm))
+
+    def set_host_threads(self, threads):
+        """Worker threads that pack host rows before the H2D copy (-1 default, 0 = copy raw rows, pack on device)."""
+        _check(self._lib.qldpc_decoder_set_host_threads(self.h, threads))
 
     def launch_info(self, side):
         out = np.zeros(8, np.int32)

@@ -14,7 +14,7 @@ CLI = os.path.join(LIBDIR, "qec_ldpc")
 
 NVCC_FLAGS = ["-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
               "-Xcompiler", "-fPIC"]
-LIB_SOURCES = ["code.cpp", "kernels.cu", "decoder.cu", "bp_global.cu"] + sorted(
+LIB_SOURCES = ["code.cpp", "host_pack.cpp", "kernels.cu", "decoder.cu", "bp_global.cu"] + sorted(
     f for f in os.listdir(CSRC) if f.startswith("bp_shape_") and f.endswith(".cu"))
 
 

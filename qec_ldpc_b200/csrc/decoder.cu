@@ -12,6 +12,9 @@
 
 #include "../../include/qldpc_b200.h"
 #include "code.h"
+#include <memory>
+
+#include "host_pack.h"
 #include "kernels.cuh"
 
 using namespace qldpc;
@@ -83,8 +86,12 @@ struct qldpc_decoder {
   cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
-  uint32_t* pin = nullptr;  // pinned host staging for the weight-W generator
+  uint32_t* pin = nullptr;  // pinned host staging: weight-W generator, host-packed rows
   size_t pin_words = 0;
+  // host-buffer entry points pack one-element-per-bit rows on the host before they cross the link (host_pack.h);
+  // host_threads: -1 = default_host_threads(), 0 = off (raw rows are copied and packed on the device)
+  int host_threads = -1;
+  std::unique_ptr<qldpc::HostPacker> packer;
   // measurement: launches per kernel class, and (when enabled) CUDA-event pairs on the launching stream
   bool timing = false;
   uint64_t launches[QLDPC_NUM_TIMERS] = {0, 0, 0, 0, 0, 0};
@@ -169,6 +176,24 @@ int ensure_pipeline(qldpc_decoder* d) {
     CU_TRY(cudaEventCreateWithFlags(&d->ev_out_free[i], cudaEventDisableTiming));
   }
   return QLDPC_OK;
+}
+
+int ensure_pin(qldpc_decoder* d, size_t words) {
+  if (words <= d->pin_words) return QLDPC_OK;
+  if (d->pin) cudaFreeHost(d->pin);
+  d->pin = nullptr;
+  d->pin_words = 0;
+  CU_TRY(cudaMallocHost((void**)&d->pin, words * sizeof(uint32_t)));
+  d->pin_words = words;
+  return QLDPC_OK;
+}
+
+// The host packer, or null when host-side packing is switched off.
+HostPacker* host_packer(qldpc_decoder* d) {
+  const int want = d->host_threads < 0 ? default_host_threads() : d->host_threads;
+  if (want <= 0) return nullptr;
+  if (!d->packer || d->packer->threads() != want) d->packer.reset(new HostPacker(want));
+  return d->packer.get();
 }
 
 int ensure_stage(qldpc_decoder* d, size_t bytes) {
@@ -637,6 +662,13 @@ int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, i
   return QLDPC_OK;
 }
 
+int qldpc_decoder_set_host_threads(qldpc_decoder* dec, int threads) {
+  if (!dec) return fail(QLDPC_ERR_ARG, "null decoder");
+  if (threads > 64) return fail(QLDPC_ERR_ARG, "at most 64 host threads");
+  dec->host_threads = threads < 0 ? -1 : threads;
+  return QLDPC_OK;
+}
+
 int qldpc_decoder_launch_info(qldpc_decoder* dec, int side, int32_t out[8]) {
   if (!dec || !out || side < 0 || side > 1) return fail(QLDPC_ERR_ARG, "bad argument");
   const DevSide& s = dec->s[side];
@@ -702,6 +734,78 @@ int qldpc_decode_batch(qldpc_decoder* dec, const uint8_t* synX, const uint8_t* s
   qldpc_decoder* d = dec;
   const int n = d->n, mX = d->s[0].m, mZ = d->s[1].m;
   const int64_t slice = std::min<int64_t>(std::min<int64_t>(d->chunk, kPipeFrames), std::max<int64_t>(nframes, 1));
+  if (HostPacker* hp = host_packer(d)) {
+    // Host-packed variant of the same pipeline: syndromes are packed on the host before the H2D copy and the
+    // corrections come back as packed words that the host threads expand to one byte per bit, so the link carries
+    // 1/8 of the bytes in both directions and pageable user buffers cost nothing extra.  While the device works on
+    // slice i the host packs slice i+1 and unpacks slice i-1.
+    const int nw = d->nw, mwX = d->s[0].mw, mwZ = d->s[1].mw;
+    const size_t in_w = (size_t)slice * (mwX + mwZ), out_w = (size_t)slice * 2 * nw;
+    const size_t dev_one = (in_w + out_w) * sizeof(uint32_t) + (size_t)9 * slice + 64;
+    rc = ensure_pin(d, 2 * (in_w + out_w));
+    if (rc) return rc;
+    rc = ensure_stage(d, 2 * ((dev_one + 15) / 16 * 16));
+    if (rc) return rc;
+    rc = ensure_pipeline(d);
+    if (rc) return rc;
+    const size_t dev_stride = (dev_one + 15) / 16 * 16;
+    auto unpack_slice = [&](int j) {  // corrections of slice j: pinned words -> the caller's byte rows
+      const int64_t o = (int64_t)j * slice;
+      const int cnt = (int)std::min<int64_t>(slice, nframes - o);
+      const uint32_t* hout = d->pin + 2 * in_w + (size_t)(j & 1) * out_w;
+      hp->unpack(hout, cnt, n, nw, outX + o * n);
+      hp->unpack(hout + (size_t)cnt * nw, cnt, n, nw, outZ + o * n);
+    };
+    int i = 0;
+    for (int64_t off = 0; off < nframes; off += slice, ++i) {
+      const int nf = (int)std::min<int64_t>(slice, nframes - off);
+      const int b = i & 1;
+      uint32_t* hin = d->pin + (size_t)b * in_w;
+      uint32_t* hout = d->pin + 2 * in_w + (size_t)b * out_w;
+      uint8_t* base = (uint8_t*)d->stage + (size_t)b * dev_stride;
+      uint32_t* din = (uint32_t*)base;
+      uint32_t* dout = din + in_w;
+      uint32_t* its = dout + out_w;               // [nf][2]
+      uint8_t* oF = (uint8_t*)(its + 2 * slice);  // [nf]
+      const size_t xw = (size_t)nf * mwX, zw = (size_t)nf * mwZ, ow = (size_t)nf * nw;
+      if (i >= 2) CU_TRY(cudaEventSynchronize(d->ev_ready[b]));  // H2D out of this pinned buffer has finished
+      hp->pack(synX + off * mX, 1, nf, mX, mwX, hin);
+      hp->pack(synZ + off * mZ, 1, nf, mZ, mwZ, hin + xw);
+      if (i >= 2) CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_free[b], 0));
+      CU_TRY(cudaMemcpyAsync(din, hin, (xw + zw) * sizeof(uint32_t), cudaMemcpyHostToDevice, d->copy_stream));
+      CU_TRY(cudaEventRecord(d->ev_ready[b], d->copy_stream));
+      CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_ready[b], 0));
+      CU_TRY(cudaMemcpyAsync(d->synX, din, xw * sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
+      CU_TRY(cudaMemcpyAsync(d->synZ, din + xw, zw * sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
+      CU_TRY(cudaEventRecord(d->ev_free[b], d->stream));
+      rc = run_bp(d, d->synX, d->synZ, nf, errorProbability, maxIterations, d->decX, d->decZ, d->sfX, d->sfZ, d->itX, d->itZ);
+      if (rc) return rc;
+      if (i >= 2) CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_out_free[b], 0));
+      CU_TRY(cudaMemcpyAsync(dout, d->decX, ow * sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
+      CU_TRY(cudaMemcpyAsync(dout + ow, d->decZ, ow * sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
+      CU_TRY(launch_merge_flags(d->sfX, d->sfZ, nf, oF, d->stream));
+      if (outIters) {
+        CU_TRY(cudaMemcpy2DAsync(its, 8, d->itX, 4, 4, (size_t)nf, cudaMemcpyDeviceToDevice, d->stream));
+        CU_TRY(cudaMemcpy2DAsync(its + 1, 8, d->itZ, 4, 4, (size_t)nf, cudaMemcpyDeviceToDevice, d->stream));
+      }
+      CU_TRY(cudaEventRecord(d->ev_done[b], d->stream));
+      CU_TRY(cudaStreamWaitEvent(d->d2h_stream, d->ev_done[b], 0));
+      // pinned out-buffer b was last read by unpack_slice(i - 2), which ran (on this thread) during iteration i - 1
+      CU_TRY(cudaMemcpyAsync(hout, dout, 2 * ow * sizeof(uint32_t), cudaMemcpyDeviceToHost, d->d2h_stream));
+      CU_TRY(cudaMemcpyAsync(outFlags + off, oF, (size_t)nf, cudaMemcpyDeviceToHost, d->d2h_stream));
+      if (outIters)
+        CU_TRY(cudaMemcpyAsync(outIters + 2 * off, its, (size_t)nf * 8, cudaMemcpyDeviceToHost, d->d2h_stream));
+      CU_TRY(cudaEventRecord(d->ev_out_free[b], d->d2h_stream));
+      if (i >= 1) {
+        CU_TRY(cudaEventSynchronize(d->ev_out_free[b ^ 1]));
+        unpack_slice(i - 1);
+      }
+    }
+    CU_TRY(cudaStreamSynchronize(d->stream));
+    CU_TRY(cudaStreamSynchronize(d->d2h_stream));
+    if (i >= 1) unpack_slice(i - 1);
+    return QLDPC_OK;
+  }
   const size_t in_bytes = (size_t)(mX + mZ) * slice;
   const size_t out_bytes = ((size_t)2 * n + 1) * slice + 15;
   const size_t it_bytes = (size_t)8 * slice;
@@ -800,13 +904,8 @@ int qldpc_get_statistics_weightw(qldpc_decoder* dec, int errorWeight, int64_t nu
   qldpc_decoder* d = dec;
   const int n = d->n, nw = d->nw;
   const size_t need = (size_t)2 * nw * std::min<int64_t>(d->chunk, std::max<int64_t>(numErrors, 1));
-  if (need > d->pin_words) {
-    if (d->pin) cudaFreeHost(d->pin);
-    d->pin = nullptr;
-    d->pin_words = 0;
-    CU_TRY(cudaMallocHost((void**)&d->pin, need * sizeof(uint32_t)));
-    d->pin_words = need;
-  }
+  rc = ensure_pin(d, need);
+  if (rc) return rc;
   std::mt19937 mt(seed);  // DecoderCPU.h:394
   CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
   for (int64_t off = 0; off < numErrors; off += d->chunk) {
@@ -844,6 +943,42 @@ static int stats_from_errors(qldpc_decoder* d, const void* xErrors, const void* 
   const int n = d->n;
   const size_t row = (size_t)n * elem;
   const int64_t slice = std::min<int64_t>(std::min<int64_t>(d->chunk, kPipeFrames), std::max<int64_t>(numErrors, 1));
+  if (HostPacker* hp = host_packer(d)) {
+    // Host-packed pipeline: while the device decodes slice i the host threads pack slice i+1 into pinned memory;
+    // only nw words per row cross the link (1/32 of the int layout), through a double-buffered device stage.
+    const int nw = d->nw;
+    const size_t hwords = 2 * (size_t)slice * nw;  // x rows then z rows of one slice
+    rc = ensure_pin(d, 2 * hwords);
+    if (rc) return rc;
+    rc = ensure_stage(d, 2 * hwords * sizeof(uint32_t));
+    if (rc) return rc;
+    rc = ensure_pipeline(d);
+    if (rc) return rc;
+    CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
+    int i = 0;
+    for (int64_t off = 0; off < numErrors; off += slice, ++i) {
+      const int nf = (int)std::min<int64_t>(slice, numErrors - off);
+      const int b = i & 1;
+      uint32_t* hbuf = d->pin + (size_t)b * hwords;
+      uint32_t* dbuf = (uint32_t*)d->stage + (size_t)b * hwords;
+      const size_t xw = (size_t)nf * nw;
+      if (i >= 2) CU_TRY(cudaEventSynchronize(d->ev_ready[b]));  // the copy out of this pinned buffer has finished
+      hp->pack((const uint8_t*)xErrors + off * row, elem, nf, n, nw, hbuf);
+      hp->pack((const uint8_t*)zErrors + off * row, elem, nf, n, nw, hbuf + xw);
+      if (i >= 2) CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_free[b], 0));
+      CU_TRY(cudaMemcpyAsync(dbuf, hbuf, 2 * xw * sizeof(uint32_t), cudaMemcpyHostToDevice, d->copy_stream));
+      CU_TRY(cudaEventRecord(d->ev_ready[b], d->copy_stream));
+      CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_ready[b], 0));
+      CU_TRY(cudaMemcpyAsync(d->errX, dbuf, xw * sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
+      CU_TRY(cudaMemcpyAsync(d->errZ, dbuf + xw, xw * sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
+      CU_TRY(cudaEventRecord(d->ev_free[b], d->stream));
+      rc = run_syndrome(d, nf);
+      if (rc) return rc;
+      rc = finish_chunk(d, nf, off, errorProbability, maxIterations, perFrameFlags, perFrameIters);
+      if (rc) return rc;
+    }
+    return read_counters(d, counters);
+  }
   const size_t half = 2 * row * (size_t)slice;  // one staging buffer: x rows then z rows
   rc = ensure_stage(d, 2 * half);
   if (rc) return rc;
@@ -890,6 +1025,21 @@ int qldpc_get_stats_from_errors_u8(qldpc_decoder* dec, const uint8_t* xErrors, c
 }
 
 // -------------------------------------------------------------------------------------------------- taps
+
+int qldpc_debug_host_pack(const void* src, int elem_size, int64_t rows, int cols, uint32_t* dst, int threads) {
+  if (!src || !dst || rows < 0 || cols < 1 || (elem_size != 1 && elem_size != 4) || threads < 1 || threads > 64)
+    return fail(QLDPC_ERR_ARG, "bad argument");
+  HostPacker hp(threads);
+  hp.pack(src, elem_size, rows, cols, (cols + 31) / 32, dst);
+  return QLDPC_OK;
+}
+
+int qldpc_debug_host_unpack(const uint32_t* src, int64_t rows, int cols, uint8_t* dst, int threads) {
+  if (!src || !dst || rows < 0 || cols < 1 || threads < 1 || threads > 64) return fail(QLDPC_ERR_ARG, "bad argument");
+  HostPacker hp(threads);
+  hp.unpack(src, rows, cols, (cols + 31) / 32, dst);
+  return QLDPC_OK;
+}
 
 int qldpc_debug_generate(qldpc_decoder* dec, uint64_t seed, uint64_t first_frame, int64_t nframes, float p,
                          uint8_t* xerr, uint8_t* zerr, uint8_t* synX, uint8_t* synZ) {

@@ -3,6 +3,7 @@ import ctypes
 import os
 import re
 
+import numpy as np
 import pytest
 
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
@@ -47,3 +48,21 @@ def test_product_does_not_touch_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".cpp", ".h")):
                 src = open(os.path.join(base, f), errors="ignore").read()
                 assert "pyoracle" not in src and "liboracle" not in src and "oracle/" not in src.replace("oracle/oracle.c restates", ""), f
+
+
+def test_host_packer_matches_numpy(qldpc):
+    """The host-side marshalling (csrc/host_pack.cpp) against numpy, for ragged widths and thread counts; no GPU."""
+    rng = np.random.default_rng(3)
+    for cols in (1, 31, 32, 33, 42, 610):
+        for dtype in (np.uint8, np.int32):
+            a = (rng.random((131, cols)) < 0.3).astype(dtype)
+            if dtype == np.int32:
+                a *= rng.integers(-7, 1 << 20, size=a.shape, dtype=np.int32) | 1  # any non-zero value is a set bit
+            nz = (a != 0)
+            ref = np.zeros((131, (cols + 31) // 32), np.uint32)
+            for c in range(cols):
+                ref[:, c >> 5] |= nz[:, c].astype(np.uint32) << np.uint32(c & 31)
+            for threads in (1, 2, 5):
+                w = qldpc.host_pack(a, threads)
+                assert np.array_equal(w, ref)
+                assert np.array_equal(qldpc.host_unpack(w, cols, threads), nz.astype(np.uint8))

@@ -379,3 +379,26 @@ def test_argument_errors_are_reported(qldpc, decoders):
     with pytest.raises(qldpc.QldpcError):
         dec.configure(0, 3, 0, 0)  # no 3-slot tile
     assert int(dec.get_statistics_depolarizing(1, 0, 10, 0.05, 20)["counters"][0]) == 10  # still usable afterwards
+
+
+def test_host_packing_paths_agree(qldpc, decoders):
+    """Host-buffer entry points give identical results whether the rows are packed by host threads before the copy
+    (default) or copied raw and packed on the device (host threads = 0); several slices, ragged last slice."""
+    gc, dec = decoders("C2", 1 << 12)
+    nf = 3 * (1 << 12) + 77
+    x, z, sx, sz = dec.debug_generate(99, 5, nf, 0.05)
+    ref = None
+    try:
+        for threads in (0, 1, 3, -1):
+            dec.set_host_threads(threads)
+            ox, oz, fl, it = dec.decode_batch(sx, sz, 0.05, 50)
+            st8 = dec.get_stats_from_errors(x, z, 0.05, 50, per_frame=True)
+            st32 = dec.get_stats_from_errors(x.astype(np.int32), z.astype(np.int32), 0.05, 50, per_frame=True)
+            got = (ox, oz, fl, it, st8["counters"], st8["flags"], st8["iters"], st32["counters"], st32["flags"])
+            if ref is None:
+                ref = got
+            for a, b in zip(got, ref):
+                assert np.array_equal(a, b)
+        assert np.array_equal(ref[4], ref[7])
+    finally:
+        dec.set_host_threads(-1)
