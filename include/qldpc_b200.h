@@ -123,7 +123,7 @@ int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, i
 /* Host-buffer entry points (qldpc_get_stats_from_errors_*, qldpc_decode_batch) convert the reference's
  * one-element-per-bit rows to packed words on the host with `threads` worker threads, so that 1/32 (int) or 1/8 (byte)
  * of the bytes cross the host-device link.  threads < 0: default (environment QLDPC_HOST_THREADS, else
- * min(16, hardware threads)); 0: off -- raw rows are copied and packed on the device (use this when many ranks share
+ * min(16, hardware threads / processes on this host as announced by the launcher), off below 6); 0: off -- raw rows are copied and packed on the device (use this when many ranks share
  * few host cores).  Marshalling only: the decode itself never runs on the host. */
 int qldpc_decoder_set_host_threads(qldpc_decoder* dec, int threads);
 /* Launch geometry in use: out[0..7] = vec (-1: global-memory path), threads, ctas_per_sm, grid, dyn_smem_bytes, regs,

@@ -5,6 +5,9 @@
 #include <algorithm>
 #include <cstdlib>
 #include <cstring>
+#ifdef __linux__
+#include <sched.h>
+#endif
 
 #if defined(__x86_64__) || defined(__i386__)
 #include <immintrin.h>
@@ -15,8 +18,22 @@ namespace qldpc {
 
 int default_host_threads() {
   if (const char* env = std::getenv("QLDPC_HOST_THREADS")) return std::max(0, std::min(64, std::atoi(env)));
-  const unsigned hw = std::thread::hardware_concurrency();
-  return (int)std::max(1u, std::min(16u, hw ? hw : 1u));
+  unsigned hw = std::thread::hardware_concurrency();
+#ifdef __linux__
+  cpu_set_t set;  // the cores this process may actually run on (containers, taskset)
+  if (sched_getaffinity(0, sizeof set, &set) == 0 && CPU_COUNT(&set) > 0) hw = (unsigned)CPU_COUNT(&set);
+#endif
+  if (hw == 0) hw = 1;
+  // one process per GPU: the launcher says how many processes share this host's cores
+  for (const char* name : {"LOCAL_WORLD_SIZE", "OMPI_COMM_WORLD_LOCAL_SIZE", "MV2_COMM_WORLD_LOCAL_SIZE"})
+    if (const char* env = std::getenv(name)) {
+      const int local = std::atoi(env);
+      if (local > 1) hw = std::max(1u, hw / (unsigned)local);
+      break;
+    }
+  // packing needs ~8 threads to outrun the raw copy over the link (profiles/r1_bench_host_pack.jsonl); with fewer
+  // cores to itself a process copies the raw rows instead
+  return hw < 6 ? 0 : (int)std::min(16u, hw);
 }
 
 // ----------------------------------------------------------------------------------------------- row kernels

@@ -36,7 +36,7 @@ class HostPacker {
   bool stop_ = false;
 };
 
-// default worker count: QLDPC_HOST_THREADS if set, else min(16, hardware threads)
+// default worker count: QLDPC_HOST_THREADS if set, else min(16, hardware threads / local ranks), 0 if that is below 6
 int default_host_threads();
 
 }  // namespace qldpc
