@@ -1,3 +1,4 @@
+"""Launch shape the heuristic picks (bp_configure) and the BP kernel rate for the three reference code sizes."""
 import sys
 sys.path.insert(0, ".")
 import qec_ldpc_b200 as q
