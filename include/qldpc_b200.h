@@ -191,6 +191,8 @@ int qldpc_decoder_get_timing(qldpc_decoder* dec, double* ms, uint64_t* launches,
 
 /* Test taps for the host-side marshalling (host_pack.h); they run without a GPU.  pack: dst[r][w] bit b =
  * (src[r][32 w + b] != 0), rows of ceil(cols/32) words; unpack: the inverse, one byte per bit. */
+int qldpc_debug_weightw_patterns(uint32_t seed, int errorWeight, int n, int64_t nframes, int threads, uint32_t* xWords,
+                                 uint32_t* zWords); /* the weight-W error stream of qldpc_get_statistics_weightw, packed rows */
 int qldpc_debug_host_pack(const void* src, int elem_size, int64_t rows, int cols, uint32_t* dst, int threads);
 int qldpc_debug_host_unpack(const uint32_t* src, int64_t rows, int cols, uint8_t* dst, int threads);
 /* Device Philox generator + syndrome kernel, unpacked to host bytes: xerr, zerr [nframes x n],

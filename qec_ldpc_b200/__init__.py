@@ -80,6 +80,7 @@ def load_library():
     L.qldpc_decoder_enable_timing.argtypes = [vp, i32]
     L.qldpc_decoder_get_timing.argtypes = [vp, vp, vp, i32]
     L.qldpc_debug_division_check.argtypes = [vp, u64, i64, vp]
+    L.qldpc_debug_weightw_patterns.argtypes = [u32, i32, i32, i64, i32, vp, vp]
     L.qldpc_debug_host_pack.argtypes = [vp, i32, i64, i32, vp, i32]
     L.qldpc_debug_host_unpack.argtypes = [vp, i64, i32, vp, i32]
     L.qldpc_debug_generate.argtypes = [vp, u64, u64, i64, f32, vp, vp, vp, vp]
@@ -105,6 +106,14 @@ def host_pack(rows, threads=4):
     out = np.zeros((a.shape[0], (a.shape[1] + 31) // 32), np.uint32)
     _check(load_library().qldpc_debug_host_pack(_ptr(a), a.dtype.itemsize, a.shape[0], a.shape[1], _ptr(out), threads))
     return out
+
+
+def weightw_patterns(seed, weight, n, nframes, threads=4):
+    """Test tap: the packed x / z rows of the reference-compatible weight-W error stream (no GPU needed)."""
+    nw = (n + 31) // 32
+    x, z = np.zeros((nframes, nw), np.uint32), np.zeros((nframes, nw), np.uint32)
+    _check(load_library().qldpc_debug_weightw_patterns(seed, weight, n, nframes, threads, _ptr(x), _ptr(z)))
+    return x, z
 
 
 def host_unpack(words, cols, threads=4):

@@ -886,15 +886,9 @@ int qldpc_get_statistics_depolarizing(qldpc_decoder* dec, uint64_t seed, uint64_
   return read_counters(d, counters);
 }
 
-// MSVC's uniform_int_distribution<int>(0, R-1) over std::mt19937: the mapping the published
-// results files were generated with; std::mt19937 itself is specified by the C++ standard.
-static inline uint32_t msvc_uniform(std::mt19937& g, uint32_t R) {
-  for (;;) {
-    const uint32_t u = (uint32_t)g();
-    if (u / R < 0xFFFFFFFFu / R || 0xFFFFFFFFu % R == R - 1) return u % R;
-  }
-}
-
+// GetStatistics(errorWeight, numErrors, ...) (DecoderCPU.h:392-530): the reference's fixed-weight generator
+// (WeightWGenerator, host_pack.h: one serial mt19937 stream, as published) feeding the device decoder.  Slices are
+// generated into two pinned buffers while the device decodes the previous slice.
 int qldpc_get_statistics_weightw(qldpc_decoder* dec, int errorWeight, int64_t numErrors, float errorProbability,
                                  int maxIterations, uint32_t seed, uint64_t* counters, uint8_t* perFrameFlags,
                                  uint32_t* perFrameIters) {
@@ -903,30 +897,37 @@ int qldpc_get_statistics_weightw(qldpc_decoder* dec, int errorWeight, int64_t nu
   if (errorWeight < 0) return fail(QLDPC_ERR_ARG, "negative error weight");
   qldpc_decoder* d = dec;
   const int n = d->n, nw = d->nw;
-  const size_t need = (size_t)2 * nw * std::min<int64_t>(d->chunk, std::max<int64_t>(numErrors, 1));
-  rc = ensure_pin(d, need);
+  const int64_t slice = std::min<int64_t>(std::min<int64_t>(d->chunk, 1 << 16), std::max<int64_t>(numErrors, 1));
+  const size_t hwords = 2 * (size_t)slice * nw;  // x rows then z rows of one slice
+  rc = ensure_pin(d, 2 * hwords);
   if (rc) return rc;
-  std::mt19937 mt(seed);  // DecoderCPU.h:394
+  rc = ensure_stage(d, 2 * hwords * sizeof(uint32_t));
+  if (rc) return rc;
+  rc = ensure_pipeline(d);
+  if (rc) return rc;
+  WeightWGenerator gen(seed, n, errorWeight);  // DecoderCPU.h:394
+  HostPacker* pool = host_packer(d);
   CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
-  for (int64_t off = 0; off < numErrors; off += d->chunk) {
-    const int nf = (int)std::min<int64_t>(d->chunk, numErrors - off);
-    uint32_t* hx = d->pin;
-    uint32_t* hz = d->pin + (size_t)nf * nw;
-    std::memset(d->pin, 0, (size_t)2 * nf * nw * sizeof(uint32_t));
-    for (int f = 0; f < nf; ++f)
-      for (int i = 0; i < errorWeight; ++i) {  // DecoderCPU.h:449-458: index, then type; collisions allowed
-        const uint32_t index = msvc_uniform(mt, (uint32_t)n);
-        const uint32_t error = msvc_uniform(mt, 3u);
-        if (error == 0 || error == 1) hx[(size_t)f * nw + (index >> 5)] |= 1u << (index & 31);
-        if (error == 2 || error == 1) hz[(size_t)f * nw + (index >> 5)] |= 1u << (index & 31);
-      }
-    CU_TRY(cudaMemcpyAsync(d->errX, hx, (size_t)nf * nw * 4, cudaMemcpyHostToDevice, d->stream));
-    CU_TRY(cudaMemcpyAsync(d->errZ, hz, (size_t)nf * nw * 4, cudaMemcpyHostToDevice, d->stream));
+  int i = 0;
+  for (int64_t off = 0; off < numErrors; off += slice, ++i) {
+    const int nf = (int)std::min<int64_t>(slice, numErrors - off);
+    const int b = i & 1;
+    uint32_t* hbuf = d->pin + (size_t)b * hwords;
+    uint32_t* dbuf = (uint32_t*)d->stage + (size_t)b * hwords;
+    const size_t xw = (size_t)nf * nw;
+    if (i >= 2) CU_TRY(cudaEventSynchronize(d->ev_ready[b]));  // the copy out of this pinned buffer has finished
+    gen.next(nf, nw, hbuf, hbuf + xw, pool);
+    if (i >= 2) CU_TRY(cudaStreamWaitEvent(d->copy_stream, d->ev_free[b], 0));
+    CU_TRY(cudaMemcpyAsync(dbuf, hbuf, 2 * xw * sizeof(uint32_t), cudaMemcpyHostToDevice, d->copy_stream));
+    CU_TRY(cudaEventRecord(d->ev_ready[b], d->copy_stream));
+    CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_ready[b], 0));
+    CU_TRY(cudaMemcpyAsync(d->errX, dbuf, xw * sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
+    CU_TRY(cudaMemcpyAsync(d->errZ, dbuf + xw, xw * sizeof(uint32_t), cudaMemcpyDeviceToDevice, d->stream));
+    CU_TRY(cudaEventRecord(d->ev_free[b], d->stream));
     rc = run_syndrome(d, nf);
     if (rc) return rc;
     rc = finish_chunk(d, nf, off, errorProbability, maxIterations, perFrameFlags, perFrameIters);
     if (rc) return rc;
-    CU_TRY(cudaStreamSynchronize(d->stream));  // the pinned buffer is rewritten for the next chunk
   }
   return read_counters(d, counters);
 }
@@ -1025,6 +1026,20 @@ int qldpc_get_stats_from_errors_u8(qldpc_decoder* dec, const uint8_t* xErrors, c
 }
 
 // -------------------------------------------------------------------------------------------------- taps
+
+int qldpc_debug_weightw_patterns(uint32_t seed, int errorWeight, int n, int64_t nframes, int threads, uint32_t* xWords,
+                                 uint32_t* zWords) {
+  if (errorWeight < 0 || n < 1 || nframes < 0 || threads < 1 || threads > 64 || !xWords || !zWords)
+    return fail(QLDPC_ERR_ARG, "bad argument");
+  HostPacker pool(threads);
+  WeightWGenerator gen(seed, n, errorWeight);
+  const int nw = (n + 31) / 32;
+  // two calls, so that the hand-over of the stream position between slices is exercised as well
+  const int64_t first = nframes / 3;
+  gen.next(first, nw, xWords, zWords, &pool);
+  gen.next(nframes - first, nw, xWords + (size_t)first * nw, zWords + (size_t)first * nw, &pool);
+  return QLDPC_OK;
+}
 
 int qldpc_debug_host_pack(const void* src, int elem_size, int64_t rows, int cols, uint32_t* dst, int threads) {
   if (!src || !dst || rows < 0 || cols < 1 || (elem_size != 1 && elem_size != 4) || threads < 1 || threads > 64)

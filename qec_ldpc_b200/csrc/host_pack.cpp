@@ -211,4 +211,109 @@ void HostPacker::unpack(const uint32_t* src, int64_t rows, int cols, int words, 
   });
 }
 
+// ----------------------------------------------------------------------------------------------- weight-W stream
+
+static uint64_t msvc_accept_limit(uint32_t R) {
+  // MSVC's uniform_int_distribution<int>(0, R-1) over a 32-bit engine keeps u iff
+  //   u / R < 0xFFFFFFFF / R  ||  0xFFFFFFFF % R == R - 1        and returns u % R
+  const uint32_t q = 0xFFFFFFFFu / R, r = 0xFFFFFFFFu % R;
+  return r == R - 1 ? (uint64_t)1 << 32 : (uint64_t)q * R;
+}
+
+WeightWGenerator::WeightWGenerator(uint32_t seed, int n, int weight) : n_(n), weight_(weight) {
+  state_[0] = seed;  // std::mt19937 seeding (ISO C++ [rand.eng.mers])
+  for (int i = 1; i < 624; ++i) state_[i] = 1812433253u * (state_[i - 1] ^ (state_[i - 1] >> 30)) + (uint32_t)i;
+  limit_n_ = msvc_accept_limit((uint32_t)n);
+  limit_3_ = msvc_accept_limit(3u);
+  magic_n_ = ~(uint64_t)0 / (uint64_t)n + 1;
+}
+
+void WeightWGenerator::refill() {
+  uint32_t* s = state_;
+  auto mix = [](uint32_t hi, uint32_t lo, uint32_t far) {
+    const uint32_t y = (hi & 0x80000000u) | (lo & 0x7FFFFFFFu);
+    return far ^ (y >> 1) ^ ((y & 1u) ? 0x9908B0DFu : 0u);
+  };
+  for (int i = 0; i < 227; ++i) s[i] = mix(s[i], s[i + 1], s[i + 397]);
+  for (int i = 227; i < 623; ++i) s[i] = mix(s[i], s[i + 1], s[i - 227]);
+  s[623] = mix(s[623], s[0], s[396]);
+  for (int i = 0; i < 624; ++i) {
+    uint32_t y = s[i];
+    y ^= y >> 11;
+    y ^= (y << 7) & 0x9D2C5680u;
+    y ^= (y << 15) & 0xEFC60000u;
+    y ^= y >> 18;
+    out_[i] = y;
+  }
+  pos_ = 0;
+}
+
+void WeightWGenerator::next(int64_t frames, int words, uint32_t* hx, uint32_t* hz, HostPacker* pool) {
+  // serial part: the accepted draws of these frames, in stream order (index, type, index, type, ...)
+  const size_t need = (size_t)frames * 2 * (size_t)weight_;
+  if (draws_.size() < need) draws_.resize(need);
+  {
+    // locals: the stores into the draw buffer must not force reloads of the generator's members
+    uint32_t* __restrict dst = draws_.data();
+    const uint32_t* __restrict src = out_;
+    const uint64_t lim[2] = {limit_n_, limit_3_};
+    size_t have = 0;
+    int pos = pos_;
+    while (have < need) {
+      if (pos == 624) {
+        refill();
+        pos = 0;
+      }
+      // Rejections are rare (n / 2^32 per index draw, 2^-32 per type draw): test the rest of the block at once and
+      // copy it when nothing is rejected; otherwise walk it word by word.
+      const int take = (int)std::min<size_t>((size_t)(624 - pos), need - have);
+      const uint32_t* blk = src + pos;
+      const int first_index = (int)(have & 1);  // offset of the first word that is an index draw
+      bool rejected = false;
+      for (int k = first_index; k < take; k += 2) rejected |= (uint64_t)blk[k] >= lim[0];
+      for (int k = first_index ^ 1; k < take; k += 2) rejected |= (uint64_t)blk[k] >= lim[1];
+      if (!rejected) {
+        std::memcpy(dst + have, blk, (size_t)take * sizeof(uint32_t));
+        have += (size_t)take;
+        pos += take;
+        continue;
+      }
+      for (int k = 0; k < take && have < need; ++k, ++pos) {
+        const uint32_t u = blk[k];
+        dst[have] = u;
+        have += (uint64_t)u < lim[have & 1];  // a rejected word is overwritten by the next one
+      }
+    }
+    pos_ = pos;
+  }
+  // parallel part: frames are independent given their position in the accepted stream
+  const int n = n_, W = weight_;
+  const uint64_t magic = magic_n_;
+  const uint32_t* draws = draws_.data();
+  auto job = [&](int id, int T) {
+    const int64_t f0 = frames * id / T, f1 = frames * (id + 1) / T;
+    std::memset(hx + (size_t)f0 * words, 0, (size_t)(f1 - f0) * words * sizeof(uint32_t));
+    std::memset(hz + (size_t)f0 * words, 0, (size_t)(f1 - f0) * words * sizeof(uint32_t));
+    for (int64_t f = f0; f < f1; ++f) {
+      const uint32_t* d = draws + (size_t)f * 2 * W;
+      uint32_t* x = hx + (size_t)f * words;
+      uint32_t* z = hz + (size_t)f * words;
+      for (int i = 0; i < W; ++i) {  // DecoderCPU.h:449-458: type 0 -> X, 1 -> X and Z, 2 -> Z; collisions allowed
+        const uint64_t low = magic * d[2 * i];
+        const uint32_t index = (uint32_t)(((unsigned __int128)low * (uint32_t)n) >> 64);  // == d[2i] % n
+        const uint32_t type = d[2 * i + 1] % 3u;
+        const uint32_t bit = 1u << (index & 31);
+        if (type != 2) x[index >> 5] |= bit;
+        if (type != 0) z[index >> 5] |= bit;
+      }
+    }
+  };
+  if (pool && pool->threads() > 1 && frames >= 4096) {
+    const int T = pool->threads();
+    pool->parallel([&](int id) { job(id, T); });
+  } else {
+    job(0, 1);
+  }
+}
+
 }  // namespace qldpc

@@ -22,6 +22,8 @@ class HostPacker {
   void pack(const void* src, int elem, int64_t rows, int cols, int words, uint32_t* dst);
   // dst[r * cols + c] = bit c of src[r * words ..] as one byte
   void unpack(const uint32_t* src, int64_t rows, int cols, int words, uint8_t* dst);
+  // runs job(id) for id = 0 .. threads()-1, id 0 on the calling thread; returns when all are done
+  void parallel(const std::function<void(int)>& job) { run(job); }
 
  private:
   void run(const std::function<void(int)>& job);
@@ -34,6 +36,28 @@ class HostPacker {
   uint64_t generation_ = 0;
   int pending_ = 0;
   bool stop_ = false;
+};
+
+// The reference's fixed-weight error generator (DecoderCPU.h:394-396,446-459): one std::mt19937 stream shared by all
+// frames, W x (qubit index uniform in [0,n), Pauli type uniform in {0,1,2}) per frame through MSVC's
+// uniform_int_distribution mapping (the one the published results files were made with).  The stream is inherently
+// serial; it is split into a serial producer (raw MT19937 words, acceptance test) and a parallel consumer (modular
+// reduction, bit setting) so that the serial part is ~2 ns per draw.
+class WeightWGenerator {
+ public:
+  WeightWGenerator(uint32_t seed, int n, int weight);
+  // next `frames` patterns, bit-packed rows of `words` 32-bit words: x rows into hx, z rows into hz
+  void next(int64_t frames, int words, uint32_t* hx, uint32_t* hz, HostPacker* pool);
+
+ private:
+  void refill();
+  uint32_t state_[624];
+  uint32_t out_[624];
+  int pos_ = 624;
+  int n_, weight_;
+  uint64_t limit_n_, limit_3_;  // a raw word is accepted for a range R iff it is below limit_R (MSVC's rejection rule)
+  uint64_t magic_n_;            // floor(2^64 / n) + 1: exact u % n by two multiplications
+  std::vector<uint32_t> draws_;
 };
 
 // default worker count: QLDPC_HOST_THREADS if set, else min(16, hardware threads / local ranks), 0 if that is below 6

@@ -66,3 +66,17 @@ def test_host_packer_matches_numpy(qldpc):
                 w = qldpc.host_pack(a, threads)
                 assert np.array_equal(w, ref)
                 assert np.array_equal(qldpc.host_unpack(w, cols, threads), nz.astype(np.uint8))
+
+
+@pytest.mark.parametrize("n,weight,seed", [(610, 30, 2719323735), (42, 5, 1), (3, 7, 99), (4072, 45, 123456789),
+                                           (6000000, 20000, 7)])
+def test_weightw_stream_matches_oracle(qldpc, oracle, n, weight, seed):
+    """The library's weight-W error stream (own MT19937 + MSVC uniform_int mapping, serial producer / parallel
+    consumers) against the oracle's restatement of DecoderCPU.h:394-396,446-459, frame by frame; no GPU.  n = 3 makes
+    the index range hit the accept-everything case of the mapping, n = 610 / 42 the rejection case; with n = 6e6 one
+    index draw in 860 is rejected (~185 rejections in this run), which exercises the word-by-word path of the producer."""
+    nf = 9001 if n < 100000 else 8
+    ox, oz = oracle.weightw_stream(seed, weight, n, nf)
+    for threads in (1, 4):
+        x, z = qldpc.weightw_patterns(seed, weight, n, nf, threads)
+        assert np.array_equal(qldpc.host_unpack(x, n), ox) and np.array_equal(qldpc.host_unpack(z, n), oz)
