@@ -228,6 +228,9 @@ WeightWGenerator::WeightWGenerator(uint32_t seed, int n, int weight) : n_(n), we
   magic_n_ = ~(uint64_t)0 / (uint64_t)n + 1;
 }
 
+#ifdef QLDPC_X86
+__attribute__((target_clones("avx2", "default")))  // the loops below vectorise; 8 lanes where the CPU has them
+#endif
 void WeightWGenerator::refill() {
   uint32_t* s = state_;
   auto mix = [](uint32_t hi, uint32_t lo, uint32_t far) {
@@ -248,71 +251,92 @@ void WeightWGenerator::refill() {
   pos_ = 0;
 }
 
-void WeightWGenerator::next(int64_t frames, int words, uint32_t* hx, uint32_t* hz, HostPacker* pool) {
-  // serial part: the accepted draws of these frames, in stream order (index, type, index, type, ...)
-  const size_t need = (size_t)frames * 2 * (size_t)weight_;
-  if (draws_.size() < need) draws_.resize(need);
-  {
-    // locals: the stores into the draw buffer must not force reloads of the generator's members
-    uint32_t* __restrict dst = draws_.data();
-    const uint32_t* __restrict src = out_;
-    const uint64_t lim[2] = {limit_n_, limit_3_};
-    size_t have = 0;
-    int pos = pos_;
-    while (have < need) {
-      if (pos == 624) {
-        refill();
-        pos = 0;
-      }
-      // Rejections are rare (n / 2^32 per index draw, 2^-32 per type draw): test the rest of the block at once and
-      // copy it when nothing is rejected; otherwise walk it word by word.
-      const int take = (int)std::min<size_t>((size_t)(624 - pos), need - have);
-      const uint32_t* blk = src + pos;
-      const int first_index = (int)(have & 1);  // offset of the first word that is an index draw
-      bool rejected = false;
-      for (int k = first_index; k < take; k += 2) rejected |= (uint64_t)blk[k] >= lim[0];
-      for (int k = first_index ^ 1; k < take; k += 2) rejected |= (uint64_t)blk[k] >= lim[1];
-      if (!rejected) {
-        std::memcpy(dst + have, blk, (size_t)take * sizeof(uint32_t));
-        have += (size_t)take;
-        pos += take;
-        continue;
-      }
-      for (int k = 0; k < take && have < need; ++k, ++pos) {
-        const uint32_t u = blk[k];
-        dst[have] = u;
-        have += (uint64_t)u < lim[have & 1];  // a rejected word is overwritten by the next one
-      }
+// serial part: the next `need` accepted draws of the stream, in order (index, type, index, type, ...)
+void WeightWGenerator::produce(uint32_t* __restrict dst, size_t need) {
+  // locals: the stores into the draw buffer must not force reloads of the generator's members
+  const uint32_t* __restrict src = out_;
+  const uint64_t lim[2] = {limit_n_, limit_3_};
+  size_t have = 0;
+  int pos = pos_;
+  while (have < need) {
+    if (pos == 624) {
+      refill();
+      pos = 0;
     }
-    pos_ = pos;
+    // Rejections are rare (n / 2^32 per index draw, 2^-32 per type draw): test the rest of the block at once and
+    // copy it when nothing is rejected; otherwise walk it word by word.
+    const int take = (int)std::min<size_t>((size_t)(624 - pos), need - have);
+    const uint32_t* blk = src + pos;
+    const int first_index = (int)(have & 1);  // offset of the first word that is an index draw
+    bool rejected = false;
+    for (int k = first_index; k < take; k += 2) rejected |= (uint64_t)blk[k] >= lim[0];
+    for (int k = first_index ^ 1; k < take; k += 2) rejected |= (uint64_t)blk[k] >= lim[1];
+    if (!rejected) {
+      std::memcpy(dst + have, blk, (size_t)take * sizeof(uint32_t));
+      have += (size_t)take;
+      pos += take;
+      continue;
+    }
+    for (int k = 0; k < take && have < need; ++k, ++pos) {
+      const uint32_t u = blk[k];
+      dst[have] = u;
+      have += (uint64_t)u < lim[have & 1];  // a rejected word is overwritten by the next one
+    }
   }
-  // parallel part: frames are independent given their position in the accepted stream
+  pos_ = pos;
+}
+
+// parallel part: frames [f0, f1) of a block whose accepted draws start at `draws`
+void WeightWGenerator::map(const uint32_t* draws, int64_t f0, int64_t f1, int words, uint32_t* hx, uint32_t* hz) const {
   const int n = n_, W = weight_;
   const uint64_t magic = magic_n_;
-  const uint32_t* draws = draws_.data();
-  auto job = [&](int id, int T) {
-    const int64_t f0 = frames * id / T, f1 = frames * (id + 1) / T;
-    std::memset(hx + (size_t)f0 * words, 0, (size_t)(f1 - f0) * words * sizeof(uint32_t));
-    std::memset(hz + (size_t)f0 * words, 0, (size_t)(f1 - f0) * words * sizeof(uint32_t));
-    for (int64_t f = f0; f < f1; ++f) {
-      const uint32_t* d = draws + (size_t)f * 2 * W;
-      uint32_t* x = hx + (size_t)f * words;
-      uint32_t* z = hz + (size_t)f * words;
-      for (int i = 0; i < W; ++i) {  // DecoderCPU.h:449-458: type 0 -> X, 1 -> X and Z, 2 -> Z; collisions allowed
-        const uint64_t low = magic * d[2 * i];
-        const uint32_t index = (uint32_t)(((unsigned __int128)low * (uint32_t)n) >> 64);  // == d[2i] % n
-        const uint32_t type = d[2 * i + 1] % 3u;
-        const uint32_t bit = 1u << (index & 31);
-        if (type != 2) x[index >> 5] |= bit;
-        if (type != 0) z[index >> 5] |= bit;
-      }
+  std::memset(hx + (size_t)f0 * words, 0, (size_t)(f1 - f0) * words * sizeof(uint32_t));
+  std::memset(hz + (size_t)f0 * words, 0, (size_t)(f1 - f0) * words * sizeof(uint32_t));
+  for (int64_t f = f0; f < f1; ++f) {
+    const uint32_t* d = draws + (size_t)f * 2 * W;
+    uint32_t* x = hx + (size_t)f * words;
+    uint32_t* z = hz + (size_t)f * words;
+    for (int i = 0; i < W; ++i) {  // DecoderCPU.h:449-458: type 0 -> X, 1 -> X and Z, 2 -> Z; collisions allowed
+      const uint64_t low = magic * d[2 * i];
+      const uint32_t index = (uint32_t)(((unsigned __int128)low * (uint32_t)n) >> 64);  // == d[2i] % n
+      const uint32_t type = d[2 * i + 1] % 3u;
+      const uint32_t bit = 1u << (index & 31);
+      if (type != 2) x[index >> 5] |= bit;
+      if (type != 0) z[index >> 5] |= bit;
     }
-  };
-  if (pool && pool->threads() > 1 && frames >= 4096) {
-    const int T = pool->threads();
-    pool->parallel([&](int id) { job(id, T); });
-  } else {
-    job(0, 1);
+  }
+}
+
+void WeightWGenerator::next(int64_t frames, int words, uint32_t* hx, uint32_t* hz, HostPacker* pool) {
+  const size_t per_frame = 2 * (size_t)weight_;
+  const int T = pool ? pool->threads() : 1;
+  if (T < 3 || frames < 4096) {  // too small to split: produce, then map on this thread
+    if (draws_.size() < (size_t)frames * per_frame) draws_.resize((size_t)frames * per_frame);
+    produce(draws_.data(), (size_t)frames * per_frame);
+    map(draws_.data(), 0, frames, words, hx, hz);
+    return;
+  }
+  // Blocks of frames go through a two-stage pipeline: the calling thread produces the draws of block k+1 while the
+  // pool's other threads map block k (two draw buffers).
+  const int64_t block = 8192;
+  const size_t cap = (size_t)block * per_frame;
+  if (draws_.size() < 2 * cap) draws_.resize(2 * cap);
+  const int64_t nblocks = (frames + block - 1) / block;
+  for (int64_t k = 0; k <= nblocks; ++k) {
+    const int64_t pf0 = k * block, pf1 = std::min(frames, pf0 + block);              // block produced in this step
+    const int64_t mf0 = (k - 1) * block, mf1 = std::min(frames, mf0 + block);        // block mapped in this step
+    uint32_t* pbuf = draws_.data() + (size_t)(k & 1) * cap;
+    const uint32_t* mbuf = draws_.data() + (size_t)((k - 1) & 1) * cap;
+    pool->parallel([&](int id) {
+      if (id == 0) {
+        if (k < nblocks) produce(pbuf, (size_t)(pf1 - pf0) * per_frame);
+      } else if (k >= 1) {
+        const int64_t cnt = mf1 - mf0, w = id - 1, W1 = T - 1;
+        const int64_t a0 = cnt * w / W1, a1 = cnt * (w + 1) / W1;
+        // rows of the block start at frame mf0; the block's draws start at mbuf
+        map(mbuf - (size_t)0, a0, a1, words, hx + (size_t)mf0 * words, hz + (size_t)mf0 * words);
+      }
+    });
   }
 }
 

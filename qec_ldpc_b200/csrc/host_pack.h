@@ -51,6 +51,8 @@ class WeightWGenerator {
 
  private:
   void refill();
+  void produce(uint32_t* dst, size_t need);
+  void map(const uint32_t* draws, int64_t f0, int64_t f1, int words, uint32_t* hx, uint32_t* hz) const;
   uint32_t state_[624];
   uint32_t out_[624];
   int pos_ = 624;

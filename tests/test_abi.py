@@ -75,7 +75,7 @@ def test_weightw_stream_matches_oracle(qldpc, oracle, n, weight, seed):
     consumers) against the oracle's restatement of DecoderCPU.h:394-396,446-459, frame by frame; no GPU.  n = 3 makes
     the index range hit the accept-everything case of the mapping, n = 610 / 42 the rejection case; with n = 6e6 one
     index draw in 860 is rejected (~185 rejections in this run), which exercises the word-by-word path of the producer."""
-    nf = 9001 if n < 100000 else 8
+    nf = 30011 if n < 100000 else 8  # several 8192-frame blocks through the producer / mapper pipeline
     ox, oz = oracle.weightw_stream(seed, weight, n, nf)
     for threads in (1, 4):
         x, z = qldpc.weightw_patterns(seed, weight, n, nf, threads)
