@@ -333,8 +333,8 @@ void WeightWGenerator::next(int64_t frames, int words, uint32_t* hx, uint32_t* h
       } else if (k >= 1) {
         const int64_t cnt = mf1 - mf0, w = id - 1, W1 = T - 1;
         const int64_t a0 = cnt * w / W1, a1 = cnt * (w + 1) / W1;
-        // rows of the block start at frame mf0; the block's draws start at mbuf
-        map(mbuf - (size_t)0, a0, a1, words, hx + (size_t)mf0 * words, hz + (size_t)mf0 * words);
+        // frame indices are relative to the block: its rows start at frame mf0, its draws at mbuf
+        map(mbuf, a0, a1, words, hx + (size_t)mf0 * words, hz + (size_t)mf0 * words);
       }
     });
   }
