@@ -31,7 +31,7 @@ static BpKernel lookup_kernel(int dc, int dv, int vec, int guard) {
 
 bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, const char** why) {
   static const char* kNoShape = "no compiled BP kernel for this (check degree, variable degree)";
-  static const char* kNoFit = "one frame of messages does not fit in shared memory (HBM-resident variant not built)";
+  static const char* kNoFit = "one frame of messages does not fit in shared memory (such codes use the HBM-resident path)";
   static const char* kBadCfg = "invalid launch configuration";
   if (!lookup_kernel(dc, dv, 1, 0)) { *why = kNoShape; return false; }
   const int E = m * dc, mw = (m + 31) / 32, nw = (n + 31) / 32;
