@@ -228,10 +228,12 @@ WeightWGenerator::WeightWGenerator(uint32_t seed, int n, int weight) : n_(n), we
   magic_n_ = ~(uint64_t)0 / (uint64_t)n + 1;
 }
 
+// One MT19937 block: the twist of the 624-word state, then the tempered outputs written to `dst`.  Returns whether
+// any output is >= `limit` (the caller's cheap test for "nothing in this block can be rejected").
 #ifdef QLDPC_X86
 __attribute__((target_clones("avx2", "default")))  // the loops below vectorise; 8 lanes where the CPU has them
 #endif
-void WeightWGenerator::refill() {
+bool WeightWGenerator::block(uint32_t* __restrict dst, uint32_t limit) {
   uint32_t* s = state_;
   auto mix = [](uint32_t hi, uint32_t lo, uint32_t far) {
     const uint32_t y = (hi & 0x80000000u) | (lo & 0x7FFFFFFFu);
@@ -240,27 +242,45 @@ void WeightWGenerator::refill() {
   for (int i = 0; i < 227; ++i) s[i] = mix(s[i], s[i + 1], s[i + 397]);
   for (int i = 227; i < 623; ++i) s[i] = mix(s[i], s[i + 1], s[i - 227]);
   s[623] = mix(s[623], s[0], s[396]);
+  uint32_t over = 0;
   for (int i = 0; i < 624; ++i) {
     uint32_t y = s[i];
     y ^= y >> 11;
     y ^= (y << 7) & 0x9D2C5680u;
     y ^= (y << 15) & 0xEFC60000u;
     y ^= y >> 18;
-    out_[i] = y;
+    dst[i] = y;
+    over |= (uint32_t)(y >= limit);
   }
+  return over != 0;
+}
+
+void WeightWGenerator::refill() {
+  block(out_, 0xFFFFFFFFu);
   pos_ = 0;
 }
 
 // serial part: the next `need` accepted draws of the stream, in order (index, type, index, type, ...)
 void WeightWGenerator::produce(uint32_t* __restrict dst, size_t need) {
-  // locals: the stores into the draw buffer must not force reloads of the generator's members
-  const uint32_t* __restrict src = out_;
+  // locals: the stores into the draw buffer must not force reloads of the generator's members (dst never aliases
+  // them; out_ itself is rewritten by refill() / memcpy below, so it is read through a plain pointer)
+  const uint32_t* src = out_;
   const uint64_t lim[2] = {limit_n_, limit_3_};
   size_t have = 0;
   int pos = pos_;
+  // both acceptance limits are within n of 2^32; below the smaller one a word is accepted whatever its role
+  const uint32_t sure = (uint32_t)std::min<uint64_t>(std::min(lim[0], lim[1]), 0xFFFFFFFFull);
   while (have < need) {
     if (pos == 624) {
-      refill();
+      if (need - have >= 624) {  // a whole block is wanted: temper it straight into the draw buffer
+        if (!block(dst + have, sure)) {
+          have += 624;
+          continue;
+        }
+        std::memcpy(out_, dst + have, sizeof out_);  // some word may be rejected: walk the block below
+      } else {
+        refill();
+      }
       pos = 0;
     }
     // Rejections are rare (n / 2^32 per index draw, 2^-32 per type draw): test the rest of the block at once and

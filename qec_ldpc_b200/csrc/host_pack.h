@@ -50,6 +50,7 @@ class WeightWGenerator {
   void next(int64_t frames, int words, uint32_t* hx, uint32_t* hz, HostPacker* pool);
 
  private:
+  bool block(uint32_t* dst, uint32_t limit);
   void refill();
   void produce(uint32_t* dst, size_t need);
   void map(const uint32_t* draws, int64_t f0, int64_t f1, int words, uint32_t* hx, uint32_t* hz) const;
