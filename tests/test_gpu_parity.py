@@ -402,3 +402,25 @@ def test_host_packing_paths_agree(qldpc, decoders):
         assert np.array_equal(ref[4], ref[7])
     finally:
         dec.set_host_threads(-1)
+
+
+def test_all_published_results_files(qldpc):
+    """Every record of every results file the current version of the reference published (188 records in
+    QEC_LDPC/results/, [2,3,6,7,2,3]/ and [4,5,10,61,9,49]/; tests/golden/kat_all.json) is reproduced counter for
+    counter by qldpc_get_statistics_weightw.  The 123 remaining records (archive/, dated directories) come from
+    earlier versions of the program and are listed in the fixture for completeness only."""
+    recs = [r for r in golden("kat_all.json") if r["group"] == "current"]
+    assert len(recs) == 188
+    decs = {}
+    for code in ("C1", "C2"):
+        gc = qldpc.Code.dense(*CODES[code], golden_matrix(code, "pcmX"), golden_matrix(code, "pcmZ"),
+                              golden_matrix(code, "iMinusP"))
+        decs[code] = qldpc.Decoder(gc, 0, 1 << 17)
+    bad = []
+    for r in recs:
+        dec = decs[{42: "C1", 610: "C2"}[r["n"]]]
+        k = dec.get_statistics_weightw(r["W"], r["count"], r["errorProbability"], r["maxit"], r["seed"])["counters"]
+        got = [int(v) for v in k[:9]]
+        if got != [r[key] for key in ["count"] + COUNTERS8]:
+            bad.append((r["source"], r["record_index"], got))
+    assert not bad, bad[:3]
