@@ -81,6 +81,21 @@ def test_published_results_files(oracle, kat):
     assert got == {key: r[key] for key in got}
 
 
+def test_published_results_files_short_records(oracle):
+    """The oracle against every third 1000-frame, 100-iteration record the reference published for the n=610 code
+    (W = 1, 4, 7, ... 58; tests/golden/kat_all.json) plus the two lightest n=42 records.  The GPU test
+    test_all_published_results_files replays all 188 records; this keeps the CPU suite within minutes."""
+    recs = [r for r in golden("kat_all.json") if r["group"] == "current"]
+    short = sorted((r for r in recs if r["count"] == 1000 and r["maxit"] == 100), key=lambda r: r["W"])
+    pick = short[::3] + [r for r in recs if r["n"] == 42 and r["W"] <= 2 and r["maxit"] == 100]
+    assert len(pick) >= 20
+    for r in pick:
+        oc = oracle_code(oracle, {42: "C1", 610: "C2"}[r["n"]])
+        k = oc.get_statistics_weightw(r["W"], r["count"], r["errorProbability"], r["maxit"], r["seed"], 0)
+        got = [int(v) for v in k[:9]]
+        assert got == [r[key] for key in ["count"] + COUNTERS8], (r["source"], r["record_index"])
+
+
 @pytest.mark.slow
 def test_published_results_file_K3(oracle):
     r = golden("kat_results.json")["K3"]
