@@ -16,7 +16,7 @@ namespace qldpc {
 typedef void (*BpKernel)(const BpArgs);
 constexpr int kMaxT = 512;
 // one translation unit per shape (bp_shape_<dc>_<dv>.cu)
-#define QLDPC_SHAPES(X) X(6, 3) X(10, 4) X(10, 5) X(8, 4) X(8, 3) X(12, 6) X(10, 3) X(12, 3) X(12, 4) X(12, 5)
+#define QLDPC_SHAPES(X) X(6, 3) X(10, 4) X(10, 5) X(8, 4) X(8, 3) X(12, 6) X(10, 3) X(12, 3) X(12, 4) X(12, 5) X(4, 2) X(6, 2) X(8, 2) X(10, 2) X(12, 2)
 #define QLDPC_DECL(DC, DV) BpKernel bp_shape_##DC##_##DV(int vec, int guard);
 QLDPC_SHAPES(QLDPC_DECL)
 #undef QLDPC_DECL

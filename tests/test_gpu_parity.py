@@ -310,7 +310,9 @@ def test_global_memory_path_matches_oracle(qldpc, oracle, code, nf):
 
 @pytest.mark.parametrize("prm,shapes", [((3, 4, 8, 13, 5, 2), ((8, 3), (8, 4))), ((6, 6, 12, 7, 3, 2), ((12, 6), (12, 6))),
                                         ((3, 4, 10, 31, 2, 2), ((10, 3), (10, 4))), ((3, 4, 12, 13, 4, 2), ((12, 3), (12, 4))),
-                                        ((5, 6, 12, 37, 11, 2), ((12, 5), (12, 6)))])
+                                        ((5, 6, 12, 37, 11, 2), ((12, 5), (12, 6))), ((2, 3, 6, 7, 2, 3), ((6, 2), (6, 3))),
+                                        ((2, 2, 4, 11, 10, 2), ((4, 2), (4, 2))), ((2, 4, 8, 13, 5, 2), ((8, 2), (8, 4))),
+                                        ((2, 5, 10, 11, 3, 2), ((10, 2), (10, 5))), ((2, 6, 12, 13, 4, 2), ((12, 2), (12, 6)))])
 def test_other_instantiated_shapes(qldpc, oracle, prm, shapes):
     """The remaining compiled (check degree, variable degree) instantiations of the tile kernel, all tile widths."""
     gc = qldpc.Code.qc(*prm)
@@ -328,7 +330,7 @@ def test_other_instantiated_shapes(qldpc, oracle, prm, shapes):
         assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))
 
 
-@pytest.mark.parametrize("prm,maxit", [((2, 2, 4, 11, 10, 2), 25), ((3, 4, 14, 13, 3, 2), 31)])
+@pytest.mark.parametrize("prm,maxit", [((3, 4, 16, 17, 2, 2), 25), ((3, 4, 14, 13, 3, 2), 31)])
 def test_shapes_without_tile_kernel_use_global_path(qldpc, oracle, prm, maxit):
     """(check degree, variable degree) pairs with no compiled tile kernel decode through the global-memory path."""
     gc = qldpc.Code.qc(*prm)
