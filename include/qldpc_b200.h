@@ -110,7 +110,9 @@ int qldpc_code_check_logical(const qldpc_code* code, const int32_t* errors2n /* 
 /* ---- decoder ------------------------------------------------------------------------------------------ */
 
 /* DecoderGPU::DecoderGPU(code), DecoderGPU.h:117-130: uploads the edge tables, allocates frame buffers for up to
- * max_frames frames per launch (larger requests are processed in chunks).  device_ordinal < 0 = current device. */
+ * max_frames frames per launch (larger requests are processed in chunks).  device_ordinal < 0 = current device.
+ * A decoder owns its device buffers, streams and host threads: use one decoder per host thread (several decoders,
+ * also on the same device, may run concurrently; a code object may be shared by any number of decoders). */
 int qldpc_decoder_create(const qldpc_code* code, int device_ordinal, int max_frames, qldpc_decoder** out);
 void qldpc_decoder_destroy(qldpc_decoder* dec);
 /* Run all work of this handle on the given cudaStream_t (NULL = the handle's own stream). */
