@@ -92,9 +92,11 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   }
   const int smem = (int)bp_smem_bytes(vec, E, m, n, mw, nw);
   if (smem > smem_optin) { *why = kBadCfg; return false; }
+  // The attribute is a per-kernel ceiling shared by every decoder of the process (several codes can use the same
+  // instantiation with different tile sizes), so it is raised to the device limit rather than to this tile's size.
   for (int guard : {0, 1, 3}) {
-    if (cudaFuncSetAttribute(lookup_kernel(dc, dv, vec, guard), cudaFuncAttributeMaxDynamicSharedMemorySize, smem) !=
-        cudaSuccess) {
+    if (cudaFuncSetAttribute(lookup_kernel(dc, dv, vec, guard), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                             smem_optin) != cudaSuccess) {
       cudaGetLastError();
       *why = kNoFit;
       return false;

@@ -426,3 +426,21 @@ def test_all_published_results_files(qldpc):
         if got != [r[key] for key in ["count"] + COUNTERS8]:
             bad.append((r["source"], r["record_index"], got))
     assert not bad, bad[:3]
+
+
+def test_decoders_of_different_codes_coexist(qldpc, oracle):
+    """Two codes that use the same kernel instantiation ((8,4): P=509 needs a 130 KB tile, P=13 a 4 KB one) decoded
+    alternately by two live decoders: the per-kernel shared-memory ceiling must not be lowered by the smaller one."""
+    big, small = (4, 4, 8, 509, 208, 2), (3, 4, 8, 13, 5, 2)
+    cb, cs = qldpc.Code.qc(*big), qldpc.Code.qc(*small)
+    db = qldpc.Decoder(cb, 0, 256)
+    ds = qldpc.Decoder(cs, 0, 4096)  # created second: configures the (8,4) kernels for its small tile
+    ob = oracle.code_qc(*big)
+    ob.set_logical(cb.dense_matrix(2))
+    osm = oracle.code_qc(*small)
+    osm.set_logical(cs.dense_matrix(2))
+    for rnd in range(2):
+        a = db.get_statistics_depolarizing(3, 100 * rnd, 48, 0.03, 30)["counters"]
+        assert np.array_equal(a, ob.run_depolarizing(3, 100 * rnd, 48, 0.03, 30)["counters"])
+        b = ds.get_statistics_depolarizing(3, 100 * rnd, 2000, 0.03, 30)["counters"]
+        assert np.array_equal(b, osm.run_depolarizing(3, 100 * rnd, 2000, 0.03, 30)["counters"])
