@@ -225,9 +225,12 @@ cudaError_t launch_syndrome(const uint32_t* errX, const uint32_t* errZ, int nfra
                             const uint16_t* vchkX, int dvX, int mwX, uint32_t* synX, const uint16_t* vchkZ, int dvZ,
                             int mwZ, uint32_t* synZ, cudaStream_t st) {
   if (nframes <= 0) return cudaSuccess;
-  const int blocks = std::min((nframes + 7) / 8, 148 * 16);
-  const size_t sh = (size_t)8 * std::max(mwX, mwZ) * sizeof(uint32_t);
-  syndrome_kernel<<<blocks, 256, sh, st>>>(errX, errZ, nframes, n, nw, vchkX, dvX, mwX, synX, vchkZ, dvZ, mwZ, synZ);
+  // one warp per frame with max(mwX, mwZ) words of shared memory each; fewer warps per block for very wide codes
+  const size_t per_warp = (size_t)std::max(mwX, mwZ) * sizeof(uint32_t);
+  const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / per_warp));
+  const int blocks = std::min((nframes + warps - 1) / warps, 148 * 16);
+  syndrome_kernel<<<blocks, 32 * warps, warps * per_warp, st>>>(errX, errZ, nframes, n, nw, vchkX, dvX, mwX, synX, vchkZ,
+                                                               dvZ, mwZ, synZ);
   return cudaGetLastError();
 }
 
@@ -358,9 +361,22 @@ __global__ void __launch_bounds__(256) stats_kernel(const StatsArgs a) {
 
 cudaError_t launch_stats(const StatsArgs& a, cudaStream_t st) {
   if (a.nframes <= 0) return cudaSuccess;
-  const int blocks = std::min((a.nframes + 7) / 8, 148 * 8);
-  const size_t sh = (size_t)8 * 2 * a.nw * sizeof(uint32_t);
-  stats_kernel<<<blocks, 256, sh, st>>>(a);
+  // one warp per frame with 2 * nw words of shared memory each (the residual); for very long codes fewer warps per
+  // block, and beyond 48 KB per block the opt-in shared-memory ceiling
+  const size_t per_warp = (size_t)2 * a.nw * sizeof(uint32_t);
+  size_t cap = 48 * 1024;
+  if (per_warp * 4 > cap) {
+    int dev = 0, optin = 0;
+    cudaGetDevice(&dev);
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, dev);
+    cap = (size_t)std::max(optin - 1024, 48 * 1024);
+    if (per_warp > cap) return cudaErrorInvalidValue;
+    cudaError_t e = cudaFuncSetAttribute(stats_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)cap);
+    if (e != cudaSuccess) return e;
+  }
+  const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, cap / per_warp));
+  const int blocks = std::min((a.nframes + warps - 1) / warps, 148 * 8);
+  stats_kernel<<<blocks, 32 * warps, warps * per_warp, st>>>(a);
   return cudaGetLastError();
 }
 
