@@ -13,7 +13,10 @@ from oracle.pyoracle import Oracle  # noqa: E402
 budget = float(sys.argv[1]) if len(sys.argv) > 1 else 120.0
 O = Oracle()
 rng = np.random.default_rng(20261018)
-codes = {"C1": (3, 3, 6, 7, 2, 3), "C2": (4, 5, 10, 61, 9, 49), "C5": (4, 4, 8, 509, 208, 2)}
+codes = {"C1": (3, 3, 6, 7, 2, 3), "C2": (4, 5, 10, 61, 9, 49), "C5": (4, 4, 8, 509, 208, 2),
+         # further kernel shapes: (8,3)/(8,4), (6,2)/(6,3), (12,5)/(12,6), (10,3)/(10,4), and (14,3)/(14,4) with no tile kernel
+         "S8": (3, 4, 8, 13, 5, 2), "S6": (2, 3, 6, 7, 2, 3), "S12": (5, 6, 12, 13, 4, 2), "S10": (3, 4, 10, 31, 2, 2),
+         "S14": (3, 4, 14, 13, 3, 2)}
 objs = {}
 for name, prm in codes.items():
     gc = q.Code.qc(*prm)
@@ -24,11 +27,11 @@ t_end = time.time() + budget
 total = 0
 case = 0
 while time.time() < t_end:
-    name = rng.choice(["C1", "C2", "C2", "C2", "C5"])
+    name = rng.choice(["C1", "C2", "C2", "C2", "C5", "S8", "S6", "S12", "S10", "S14"])
     gc, oc, dec = objs[name]
     p = float(np.float32(rng.choice([0.005, 0.01, 0.02, 0.03, 0.05, 0.07, 0.1, 0.2, 1e-6])))
     maxit = int(rng.choice([1, 3, 10, 11, 20, 37, 50, 100]))
-    nf = {"C1": 20000, "C2": 4000, "C5": 300}[name]
+    nf = {"C1": 20000, "C2": 4000, "C5": 300}.get(name, 6000)
     seed = int(rng.integers(0, 2**62))
     first = int(rng.integers(0, 2**40))
     vec = int(rng.choice([0, 4, 2, 1, -1]))
