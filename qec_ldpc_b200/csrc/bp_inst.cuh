@@ -1,18 +1,20 @@
 // Explicit instantiation of the BP tile kernel for one (check degree, variable degree) shape: tile widths 1/2/4 and
 // the three division-guard variants.  One translation unit per shape so that nvcc builds them in parallel.
+// A shape may add instantiations with the number of checks as a compile-time constant (QLDPC_DEFINE_SHAPE_M): the
+// check-phase addresses of such a kernel are immediates; it is picked when the code's check count matches.
 #pragma once
 #include "bp_kernel.cuh"
 
 namespace qldpc {
 typedef void (*BpKernel)(const BpArgs);
 
-template <int DC, int DV>
+template <int DC, int DV, int M>
 BpKernel bp_kernel_for(int vec, int guard) {
 #define QLDPC_V(V)                                                                  \
   if (vec == V) {                                                                   \
-    if (guard == 0) return bp_tile_kernel<DC, DV, V, 0>;              \
-    if (guard == 1) return bp_tile_kernel<DC, DV, V, 1>;              \
-    return bp_tile_kernel<DC, DV, V, 3>;                              \
+    if (guard == 0) return bp_tile_kernel<DC, DV, V, 0, M>;           \
+    if (guard == 1) return bp_tile_kernel<DC, DV, V, 1, M>;           \
+    return bp_tile_kernel<DC, DV, V, 3, M>;                           \
   }
   QLDPC_V(4) QLDPC_V(2) QLDPC_V(1)
 #undef QLDPC_V
@@ -21,4 +23,11 @@ BpKernel bp_kernel_for(int vec, int guard) {
 }  // namespace qldpc
 
 #define QLDPC_DEFINE_SHAPE(DC, DV) \
-  namespace qldpc { BpKernel bp_shape_##DC##_##DV(int vec, int guard) { return bp_kernel_for<DC, DV>(vec, guard); } }
+  namespace qldpc { BpKernel bp_shape_##DC##_##DV(int vec, int guard, int) { return bp_kernel_for<DC, DV, 0>(vec, guard); } }
+#define QLDPC_DEFINE_SHAPE_M(DC, DV, M)                                       \
+  namespace qldpc {                                                           \
+  BpKernel bp_shape_##DC##_##DV(int vec, int guard, int m) {                  \
+    if (m == M) return bp_kernel_for<DC, DV, M>(vec, guard);                  \
+    return bp_kernel_for<DC, DV, 0>(vec, guard);                              \
+  }                                                                           \
+  }

@@ -1,2 +1,2 @@
 #include "bp_inst.cuh"
-QLDPC_DEFINE_SHAPE(10, 4)
+QLDPC_DEFINE_SHAPE_M(10, 4, 244)

@@ -17,13 +17,13 @@ typedef void (*BpKernel)(const BpArgs);
 constexpr int kMaxT = 512;
 // one translation unit per shape (bp_shape_<dc>_<dv>.cu)
 #define QLDPC_SHAPES(X) X(6, 3) X(10, 4) X(10, 5) X(8, 4) X(8, 3) X(12, 6) X(10, 3) X(12, 3) X(12, 4) X(12, 5) X(4, 2) X(6, 2) X(8, 2) X(10, 2) X(12, 2)
-#define QLDPC_DECL(DC, DV) BpKernel bp_shape_##DC##_##DV(int vec, int guard);
+#define QLDPC_DECL(DC, DV) BpKernel bp_shape_##DC##_##DV(int vec, int guard, int m);
 QLDPC_SHAPES(QLDPC_DECL)
 #undef QLDPC_DECL
 
-static BpKernel lookup_kernel(int dc, int dv, int vec, int guard) {
+static BpKernel lookup_kernel(int dc, int dv, int vec, int guard, int m) {
 #define QLDPC_CASE(DC, DV) \
-  if (dc == DC && dv == DV) return bp_shape_##DC##_##DV(vec, guard);
+  if (dc == DC && dv == DV) return bp_shape_##DC##_##DV(vec, guard, m);
   QLDPC_SHAPES(QLDPC_CASE)
 #undef QLDPC_CASE
   return nullptr;
@@ -33,7 +33,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   static const char* kNoShape = "no compiled BP kernel for this (check degree, variable degree)";
   static const char* kNoFit = "one frame of messages does not fit in shared memory (such codes use the HBM-resident path)";
   static const char* kBadCfg = "invalid launch configuration";
-  if (!lookup_kernel(dc, dv, 1, 0)) { *why = kNoShape; return false; }
+  if (!lookup_kernel(dc, dv, 1, 0, m)) { *why = kNoShape; return false; }
   const int E = m * dc, mw = (m + 31) / 32, nw = (n + 31) / 32;
   if (E >= 65536) { *why = kNoFit; return false; }
   int dev = 0, smem_optin = 0, smem_sm = 0;
@@ -48,7 +48,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
     int r = 0;
     for (int guard : {0, 1, 3}) {
       cudaFuncAttributes fa;
-      if (cudaFuncGetAttributes(&fa, lookup_kernel(dc, dv, v, guard)) == cudaSuccess) r = std::max(r, fa.numRegs);
+      if (cudaFuncGetAttributes(&fa, lookup_kernel(dc, dv, v, guard, m)) == cudaSuccess) r = std::max(r, fa.numRegs);
     }
     cudaGetLastError();
     return std::max(r, 32);
@@ -95,7 +95,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   // The attribute is a per-kernel ceiling shared by every decoder of the process (several codes can use the same
   // instantiation with different tile sizes), so it is raised to the device limit rather than to this tile's size.
   for (int guard : {0, 1, 3}) {
-    if (cudaFuncSetAttribute(lookup_kernel(dc, dv, vec, guard), cudaFuncAttributeMaxDynamicSharedMemorySize,
+    if (cudaFuncSetAttribute(lookup_kernel(dc, dv, vec, guard, m), cudaFuncAttributeMaxDynamicSharedMemorySize,
                              smem_optin) != cudaSuccess) {
       cudaGetLastError();
       *why = kNoFit;
@@ -103,7 +103,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
     }
   }
   const int regs = regs_of(vec);
-  BpKernel k = lookup_kernel(dc, dv, vec, 3);
+  BpKernel k = lookup_kernel(dc, dv, vec, 3, m);
   if (threads % 32 || threads < 32 || threads > kMaxT) { *why = kBadCfg; return false; }
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem) != cudaSuccess || occ < 1) {
@@ -123,7 +123,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
 }
 
 cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, int guard, cudaStream_t st) {
-  BpKernel k = lookup_kernel(dc, dv, cfg.vec, guard);
+  BpKernel k = lookup_kernel(dc, dv, cfg.vec, guard, args.m);
   if (!k) return cudaErrorInvalidDeviceFunction;
   const int tiles = (nframes + cfg.vec - 1) / cfg.vec;
   const int grid = std::max(1, std::min(cfg.grid, tiles));
