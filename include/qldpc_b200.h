@@ -98,7 +98,8 @@ int qldpc_code_exponents(const qldpc_code* code, int side, int32_t* out /* [J*L]
 int qldpc_code_csr(const qldpc_code* code, int side, int32_t* chk_var /* [m*dc], ascending variable */);
 int qldpc_code_csc(const qldpc_code* code, int side, int32_t* var_chk /* [n*dv], ascending check */,
                    int32_t* var_edge /* [n*dv] check-major edge id e*dc+i, may be NULL */);
-/* which: 0 pcmX, 1 pcmZ, 2 logical-check matrix in use [logical_rows x 2n]. */
+/* which: 0 pcmX, 1 pcmZ, 2 logical-check matrix in use [logical_rows x 2n] (row-reduced), 3 iMinusP in the reference's
+ * shape [2n x 2n]: the matrix as supplied (file / caller) when there is one, else the generated rows padded with zero rows. */
 int qldpc_code_dense(const qldpc_code* code, int which, int32_t* out);
 /* 1 if pcmX * pcmZ^T == 0 (mod 2), 0 if not (the reference never checks). */
 int qldpc_code_is_css(const qldpc_code* code);
@@ -125,9 +126,11 @@ int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, i
 /* Host-buffer entry points (qldpc_get_stats_from_errors_*, qldpc_decode_batch) convert the reference's
  * one-element-per-bit rows to packed words on the host with `threads` worker threads, so that 1/32 (int) or 1/8 (byte)
  * of the bytes cross the host-device link.  threads < 0: default (environment QLDPC_HOST_THREADS, else
- * min(16, hardware threads / processes on this host as announced by the launcher), off below 6); 0: off -- raw rows are copied and packed on the device (use this when many ranks share
- * few host cores).  Marshalling only: the decode itself never runs on the host. */
+ * min(16, hardware threads / processes on this host as announced by the launcher), at least 1); 0: off -- raw rows
+ * are copied and packed on the device.  Batches of at most 2048 frames of qldpc_decode_batch take a low-latency path
+ * without host threads.  Marshalling only: the decode itself never runs on the host. */
 int qldpc_decoder_set_host_threads(qldpc_decoder* dec, int threads);
+int qldpc_default_host_threads(void); /* the default described above, for this process */
 /* Launch geometry in use: out[0..7] = vec (-1: global-memory path), threads, ctas_per_sm, grid, dyn_smem_bytes, regs,
  * SM count, frames per launch. */
 int qldpc_decoder_launch_info(qldpc_decoder* dec, int side, int32_t out[8]);
@@ -197,6 +200,9 @@ int qldpc_debug_weightw_patterns(uint32_t seed, int errorWeight, int n, int64_t 
                                  uint32_t* zWords); /* the weight-W error stream of qldpc_get_statistics_weightw, packed rows */
 int qldpc_debug_host_pack(const void* src, int elem_size, int64_t rows, int cols, uint32_t* dst, int threads);
 int qldpc_debug_host_unpack(const uint32_t* src, int64_t rows, int cols, uint8_t* dst, int threads);
+/* Streaming read of a host buffer with `threads` of the packer's worker threads (its access pattern without the
+ * arithmetic), best of `repeats`: the measured host-memory bandwidth behind bench.py's e2e.host_mem_roofline. */
+int qldpc_debug_host_read_gbs(const void* src, int64_t bytes, int threads, int repeats, double* gbs);
 /* Device Philox generator + syndrome kernel, unpacked to host bytes: xerr, zerr [nframes x n],
  * synX [nframes x mX], synZ [nframes x mZ] (any may be NULL). */
 int qldpc_debug_generate(qldpc_decoder* dec, uint64_t seed, uint64_t first_frame, int64_t nframes, float p,

@@ -83,6 +83,7 @@ def load_library():
     L.qldpc_debug_weightw_patterns.argtypes = [u32, i32, i32, i64, i32, vp, vp]
     L.qldpc_debug_host_pack.argtypes = [vp, i32, i64, i32, vp, i32]
     L.qldpc_debug_host_unpack.argtypes = [vp, i64, i32, vp, i32]
+    L.qldpc_debug_host_read_gbs.argtypes = [vp, i64, i32, i32, C.POINTER(C.c_double)]
     L.qldpc_debug_generate.argtypes = [vp, u64, u64, i64, f32, vp, vp, vp, vp]
     L.qldpc_debug_bp_trace.argtypes = [vp, i32, vp, i32, f32, i32, i32, vp, vp, vp]
     _lib = L
@@ -114,6 +115,18 @@ def weightw_patterns(seed, weight, n, nframes, threads=4):
     x, z = np.zeros((nframes, nw), np.uint32), np.zeros((nframes, nw), np.uint32)
     _check(load_library().qldpc_debug_weightw_patterns(seed, weight, n, nframes, threads, _ptr(x), _ptr(z)))
     return x, z
+
+
+def host_read_gbs(ptr, nbytes, threads, repeats=3):
+    """Measured streaming-read bandwidth (GB/s) of a host buffer with the packer's worker threads."""
+    out = C.c_double(0.0)
+    _check(load_library().qldpc_debug_host_read_gbs(C.c_void_p(ptr), nbytes, threads, repeats, C.byref(out)))
+    return out.value
+
+
+def default_host_threads():
+    """Worker threads the host-buffer entry points use by default on this process (host_pack.h)."""
+    return int(load_library().qldpc_default_host_threads())
 
 
 def host_unpack(words, cols, threads=4):
@@ -197,7 +210,7 @@ class Code:
         return a, b
 
     def dense_matrix(self, which):
-        shape = [(self.mX, self.n), (self.mZ, self.n), (self.logical_rows, 2 * self.n)][which]
+        shape = [(self.mX, self.n), (self.mZ, self.n), (self.logical_rows, 2 * self.n), (2 * self.n, 2 * self.n)][which]
         out = np.zeros(shape, np.int32)
         _check(self._lib.qldpc_code_dense(self.h, which, _ptr(out)))
         return out

@@ -29,8 +29,12 @@ class Decoder {
   explicit Decoder(Quantum_LDPC_Code code) : _code(code) {}
   virtual ~Decoder() {}
 
+  // Not pure, like the reference's (Decoder.h:40-43): the base does nothing and reports SUCCESS.
   virtual ErrorCode Decode(const IntArray1d_h& syndromeX, const IntArray1d_h& syndromeZ, float errorProbability,
-                           int maxIterations, IntArray1d_h& outErrorsX, IntArray1d_h& outErrorsZ) = 0;
+                           int maxIterations, IntArray1d_h& outErrorsX, IntArray1d_h& outErrorsZ) {
+    (void)syndromeX; (void)syndromeZ; (void)errorProbability; (void)maxIterations; (void)outErrorsX; (void)outErrorsZ;
+    return SUCCESS;
+  }
 
   // Seeded and unseeded forms (the unseeded one draws its seed from std::random_device, DecoderCPU.h:532-537).
   virtual CodeStatistics GetStatistics(int errorWeight, int numErrors, float errorProbability, int maxIterations,

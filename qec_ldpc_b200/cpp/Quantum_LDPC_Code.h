@@ -32,7 +32,7 @@ class Quantum_LDPC_Code {
   Quantum_LDPC_Code(qldpc_code* h, const qldpc_code_info& i)
       : _handle(std::make_shared<Owner>(h)), J(i.J), K(i.K), L(i.L), P(i.P), sigma(i.sigma), tau(i.tau), n(i.n),
         numEqsX(i.mX), numEqsZ(i.mZ), pcmX(denseOf(h, 0, i.mX, i.n)), pcmZ(denseOf(h, 1, i.mZ, i.n)),
-        iMinusP(denseOf(h, 2, i.logical_rows, 2 * i.n)) {}
+        iMinusP(denseOf(h, 3, 2 * i.n, 2 * i.n)) {}
   explicit Quantum_LDPC_Code(qldpc_code* h) : Quantum_LDPC_Code(h, infoOf(h)) {}
 
  public:
@@ -40,8 +40,9 @@ class Quantum_LDPC_Code {
   const int n;  // number of physical qubits = L*P
   const int numEqsX, numEqsZ;
   IntArray2d_h pcmX, pcmZ;
-  // Logical-check matrix in use: the row-reduced iMinusP of the code file (same kernel, hence same decisions), or the
-  // generated equivalent for codes built from (J,K,L,P,sigma,tau).
+  // 2n x 2n like the reference's (Quantum_LDPC_Code.h:16): the iMinusP of the code file / constructor argument as it was
+  // given, or -- for codes built from (J,K,L,P,sigma,tau) alone -- the generated logical-check rows (a basis of
+  // ker(pcmX) and of ker(pcmZ): same kernel, hence the same decisions) followed by zero rows.
   IntArray2d_h iMinusP;
 
   // Quantum_LDPC_Code.h:26-80; throws std::string like the reference (:78).
@@ -79,6 +80,14 @@ class Quantum_LDPC_Code {
  private:
   static qldpc_code* fromDense(int J, int K, int L, int P, int sigma, int tau, const IntArray2d_h& x, const IntArray2d_h& z,
                                const IntArray2d_h& imp) {
+    const size_t nn = (size_t)L * (size_t)P;
+    auto shaped = [](const IntArray2d_h& m, size_t rows, size_t cols) {
+      return m.num_rows == rows && m.num_cols == cols && m.values.size() == rows * cols;
+    };
+    if (J < 1 || K < 1 || L < 1 || P < 1) throw std::string("Quantum_LDPC_Code: J, K, L, P must be positive");
+    if (!shaped(x, (size_t)J * P, nn)) throw std::string("Quantum_LDPC_Code: pcmX must be (J*P) x (L*P)");
+    if (!shaped(z, (size_t)K * P, nn)) throw std::string("Quantum_LDPC_Code: pcmZ must be (K*P) x (L*P)");
+    if (!imp.values.empty() && !shaped(imp, 2 * nn, 2 * nn)) throw std::string("Quantum_LDPC_Code: iMinusP must be (2*L*P) x (2*L*P)");
     qldpc_code* h = nullptr;
     const int32_t* ip = imp.values.empty() ? nullptr : imp.values.data();
     if (qldpc_code_create_dense(J, K, L, P, sigma, tau, x.values.data(), z.values.data(), ip, &h) != QLDPC_OK)

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 
 #include <algorithm>
+#include <chrono>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -84,6 +85,22 @@ struct qldpc_decoder {
   size_t stage_bytes = 0;
   // host-buffer entry points run as a pipeline: H2D of the next slice and D2H of the previous one overlap the decode
   cudaStream_t copy_stream = nullptr, d2h_stream = nullptr;
+  // the Z-side BP launch of a small batch or pipeline slice runs beside the X side on its own stream, so that the
+  // straggler tail of one kernel overlaps the start of the other
+  cudaStream_t side_stream = nullptr;
+  cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  uint8_t* small_pin = nullptr;  // pinned staging of the low-latency Decode path
+  size_t small_pin_bytes = 0;
+  // the low-latency path replays a captured CUDA graph when the call repeats the previous one's shape (a per-frame
+  // Decode loop): one graph launch instead of nine stream operations
+  struct SmallGraph {
+    cudaGraphExec_t exec = nullptr;
+    int nf = 0, maxit = 0;
+    uint32_t p_bits = 0;
+    const void *stage = nullptr, *pin = nullptr;
+    int cfg_epoch = -1;
+  } small_graph;
+  int cfg_epoch = 0;  // bumped by every qldpc_decoder_configure
   cudaEvent_t ev_ready[2] = {nullptr, nullptr}, ev_free[2] = {nullptr, nullptr};
   cudaEvent_t ev_done[2] = {nullptr, nullptr}, ev_out_free[2] = {nullptr, nullptr};
   uint32_t* pin = nullptr;  // pinned host staging: weight-W generator, host-packed rows
@@ -110,6 +127,11 @@ struct qldpc_decoder {
     cudaFree(sfX); cudaFree(sfZ); cudaFree(fflags); cudaFree(itX); cudaFree(itZ);
     cudaFree(counters); cudaFree(queues); cudaFree(lx); cudaFree(lz); cudaFree(lm); cudaFree(stage);
     if (pin) cudaFreeHost(pin);
+    if (small_graph.exec) cudaGraphExecDestroy(small_graph.exec);
+    if (small_pin) cudaFreeHost(small_pin);
+    if (ev_fork) cudaEventDestroy(ev_fork);
+    if (ev_join) cudaEventDestroy(ev_join);
+    if (side_stream) cudaStreamDestroy(side_stream);
     for (int i = 0; i < 2; ++i) {
       if (ev_ready[i]) cudaEventDestroy(ev_ready[i]);
       if (ev_free[i]) cudaEventDestroy(ev_free[i]);
@@ -131,7 +153,8 @@ struct Timed {
   qldpc_decoder* d;
   int cls;
   cudaEvent_t a = nullptr, b = nullptr;
-  Timed(qldpc_decoder* d_, int cls_, int n = 1) : d(d_), cls(cls_) {
+  cudaStream_t st;
+  Timed(qldpc_decoder* d_, int cls_, int n = 1, cudaStream_t st_ = nullptr) : d(d_), cls(cls_), st(st_ ? st_ : d_->stream) {
     d->launches[cls] += (uint64_t)n;
     if (!d->timing) return;
     auto get = [&]() {
@@ -142,11 +165,11 @@ struct Timed {
     };
     a = get();
     b = get();
-    cudaEventRecord(a, d->stream);
+    cudaEventRecord(a, st);
   }
   ~Timed() {
     if (!a) return;
-    cudaEventRecord(b, d->stream);
+    cudaEventRecord(b, st);
     d->pending.push_back({cls, a, b});
   }
 };
@@ -162,8 +185,38 @@ void drain_timing(qldpc_decoder* d) {
   cudaGetLastError();
 }
 
-// Slice size of the host-buffer pipelines (frames).
+// Largest slice of the host-buffer pipelines (frames).  The first slice cannot overlap anything (the host packs it
+// while the device idles), so the slices start small and grow by a quarter per slice up to this size (slice_frames):
+// packing slice i+1 then takes no longer than decoding slice i (host packing runs at 0.7-0.9 of the decode rate), so
+// the device idles only for the first, small slice.
 const int kPipeFrames = 1 << 17;
+const int kFirstSlice = 1 << 13;
+// batches up to this many frames take the low-latency Decode path (one stream, no host threads, no pipeline)
+const int kSmallBatch = 2048;
+
+int64_t slice_frames(int index, int64_t max_slice) {
+  int64_t s = kFirstSlice;
+  for (int i = 0; i < index && s < max_slice; ++i) s = (s + s / 4 + 1023) / 1024 * 1024;
+  return std::min<int64_t>(s, max_slice);
+}
+
+// Waits for everything a pipelined call may still have in flight (error exits: the caller's buffers and the pinned
+// staging must not be touched by asynchronous copies after the call has returned).
+void quiesce(qldpc_decoder* d) {
+  if (d->stream) cudaStreamSynchronize(d->stream);
+  if (d->copy_stream) cudaStreamSynchronize(d->copy_stream);
+  if (d->d2h_stream) cudaStreamSynchronize(d->d2h_stream);
+  if (d->side_stream) cudaStreamSynchronize(d->side_stream);
+  cudaGetLastError();
+}
+
+int ensure_side_stream(qldpc_decoder* d) {
+  if (d->side_stream) return QLDPC_OK;
+  CU_TRY(cudaStreamCreateWithFlags(&d->side_stream, cudaStreamNonBlocking));
+  CU_TRY(cudaEventCreateWithFlags(&d->ev_fork, cudaEventDisableTiming));
+  CU_TRY(cudaEventCreateWithFlags(&d->ev_join, cudaEventDisableTiming));
+  return QLDPC_OK;
+}
 
 int ensure_pipeline(qldpc_decoder* d) {
   if (d->copy_stream) return QLDPC_OK;
@@ -313,10 +366,19 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
   if (nf <= 0) return QLDPC_OK;
   const float prior = 2.0f / 3.0f * errorProbability;  // DecoderCPU.h:259, same float expression
   CU_TRY(cudaMemsetAsync(d->queues, 0, 2 * sizeof(unsigned int), d->stream));
+  // Slices and small batches: the Z side runs beside the X side on a second stream (its CTAs move in as the X side's
+  // drain); full-size launches run back to back, where the tail is negligible and per-kernel timing stays clean.
+  const bool overlap = only_side < 0 && nf <= (1 << 18) && !trace_q && !trace_r && !d->s[0].use_global &&
+                       !d->s[1].use_global && ensure_side_stream(d) == QLDPC_OK;
+  if (overlap) {
+    CU_TRY(cudaEventRecord(d->ev_fork, d->stream));
+    CU_TRY(cudaStreamWaitEvent(d->side_stream, d->ev_fork, 0));
+  }
   for (int side = 0; side < 2; ++side) {
     if (only_side >= 0 && side != only_side) continue;
     DevSide& s = d->s[side];
     if (!s.cfg_ok) return fail(QLDPC_ERR_UNSUPPORTED, s.cfg_err);
+    cudaStream_t st = overlap && side == 1 ? d->side_stream : d->stream;
     BpArgs a;
     a.syn = side ? synZ : synX;
     a.dec = side ? decZ : decX;
@@ -329,7 +391,7 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
     a.maxit = maxIterations;
     a.prior = prior;
     a.trace_q = trace_q; a.trace_r = trace_r; a.trace_cap = trace_cap;
-    Timed t(d, side ? QLDPC_T_BP_Z : QLDPC_T_BP_X);
+    Timed t(d, side ? QLDPC_T_BP_Z : QLDPC_T_BP_X, 1, st);
     if (s.use_global) {
       if (trace_q || trace_r) return fail(QLDPC_ERR_UNSUPPORTED, "message taps are not available on the global-memory path");
       GlobalBpArgs g;
@@ -340,7 +402,11 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
       CU_TRY(global_bp_run(g, a.syn, a.dec, a.flags, a.iters, nf, nullptr, d->stream));
       continue;
     }
-    CU_TRY(bp_launch(s.dc, s.dv, s.cfg, a, nf, division_guard(prior, s.dv), d->stream));
+    CU_TRY(bp_launch(s.dc, s.dv, s.cfg, a, nf, division_guard(prior, s.dv), st));
+  }
+  if (overlap) {
+    CU_TRY(cudaEventRecord(d->ev_join, d->side_stream));
+    CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_join, 0));
   }
   return QLDPC_OK;
 }
@@ -364,6 +430,21 @@ int run_syndrome(qldpc_decoder* d, int nf) {
   CU_TRY(launch_syndrome(d->errX, d->errZ, nf, d->n, d->nw, d->s[0].vchk, d->s[0].dv, d->s[0].mw, d->synX, d->s[1].vchk,
                          d->s[1].dv, d->s[1].mw, d->synZ, d->stream));
   return QLDPC_OK;
+}
+
+// Philox depolarizing errors of nf frames and their syndromes, one kernel (errors only when with_syndrome is false).
+int run_syndrome(qldpc_decoder* d, int nf);
+
+int run_generate(qldpc_decoder* d, uint64_t seed, uint64_t first_frame, int nf, const Thresholds& thr) {
+  // the fused kernel lists error positions in 16 bits; longer codes generate and form syndromes in two launches
+  const bool fused = d->n <= 65535;
+  {
+    Timed t(d, QLDPC_T_GENERATE);
+    CU_TRY(launch_generate_syndrome(seed, first_frame, nf, d->n, d->nw, thr, d->errX, d->errZ, d->s[0].vchk, d->s[0].dv,
+                                    d->s[0].mw, fused ? d->synX : nullptr, d->s[1].vchk, d->s[1].dv, d->s[1].mw, d->synZ,
+                                    d->stream));
+  }
+  return fused ? QLDPC_OK : run_syndrome(d, nf);
 }
 
 int check_common(qldpc_decoder* d, int64_t nframes, int maxIterations) {
@@ -515,10 +596,18 @@ int qldpc_code_csc(const qldpc_code* code, int side, int32_t* var_chk, int32_t* 
 }
 
 int qldpc_code_dense(const qldpc_code* code, int which, int32_t* out) {
-  if (!code || !out || which < 0 || which > 2) return fail(QLDPC_ERR_ARG, "bad argument");
+  if (!code || !out || which < 0 || which > 3) return fail(QLDPC_ERR_ARG, "bad argument");
   const Code& c = *code->c;
   if (which < 2) {
     c.dense_pcm(which, out);
+  } else if (which == 3) {
+    // the reference's shape contract: iMinusP is 2n x 2n (Quantum_LDPC_Code.h:16,60-74).  The matrix as it was
+    // supplied when there is one, else the generated logical-check rows followed by zero rows (same kernel).
+    const BitMatrix& src = c.iminusp_raw.rows ? c.iminusp_raw : c.logical;
+    const int w = 2 * c.n;
+    std::fill(out, out + (size_t)w * w, 0);
+    for (int r = 0; r < src.rows && r < w; ++r)
+      for (int col = 0; col < w; ++col) out[(size_t)r * w + col] = src.get(r, col);
   } else {
     for (int r = 0; r < c.logical.rows; ++r)
       for (int col = 0; col < 2 * c.n; ++col) out[(size_t)r * 2 * c.n + col] = c.logical.get(r, col);
@@ -587,11 +676,9 @@ int qldpc_decoder_create(const qldpc_code* code, int device_ordinal, int max_fra
     const SideTables& t = d->code.side[side];
     DevSide& s = d->s[side];
     s.m = t.m; s.dc = t.dc; s.dv = t.dv; s.E = t.E; s.mw = (t.m + 31) / 32;
-    if (t.m > 65535) {
-      s.cfg_ok = false;
-      s.cfg_err = "more than 65535 checks per side";
-      continue;
-    }
+    // the device tables hold check and message-row indices in 16 bits (syndrome_kernel, generate_syndrome_kernel and
+    // the BP kernels all read them): a side beyond that is rejected here, before anything can be launched on it
+    if (t.m > 65535) return bail(fail(QLDPC_ERR_UNSUPPORTED, "more than 65535 checks per side"));
     std::vector<uint16_t> vrow((size_t)t.E), vchk((size_t)t.E);
     for (int v = 0; v < n; ++v)
       for (int k = 0; k < t.dv; ++k) {
@@ -644,6 +731,7 @@ int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, i
   CU_TRY(cudaSetDevice(dec->device));
   BpLaunch keep = dec->s[side].user;
   const bool keep_force = dec->s[side].force_global;
+  ++dec->cfg_epoch;
   dec->s[side].force_global = frames_per_tile < 0;
   if (frames_per_tile < 0) frames_per_tile = 0;
   dec->s[side].user = BpLaunch();
@@ -668,6 +756,8 @@ int qldpc_decoder_set_host_threads(qldpc_decoder* dec, int threads) {
   dec->host_threads = threads < 0 ? -1 : threads;
   return QLDPC_OK;
 }
+
+int qldpc_default_host_threads(void) { return default_host_threads(); }
 
 int qldpc_decoder_launch_info(qldpc_decoder* dec, int side, int32_t out[8]) {
   if (!dec || !out || side < 0 || side > 1) return fail(QLDPC_ERR_ARG, "bad argument");
@@ -721,12 +811,124 @@ int qldpc_decode_batch_device(qldpc_decoder* dec, const uint32_t* d_synX, const 
   return QLDPC_OK;
 }
 
+// Low-latency Decode for small batches (the call a reference-style per-frame loop makes, DecoderCPU.h:477): no host
+// threads, no pipeline -- the syndromes go through one pinned staging buffer and one H2D copy, one launch packs both
+// sides, the X and Z BP kernels run side by side on two streams, one launch produces everything the frames return,
+// one D2H copy brings it back.
+static int decode_small(qldpc_decoder* d, const uint8_t* synX, const uint8_t* synZ, int nf, float errorProbability,
+                        int maxIterations, uint8_t* outX, uint8_t* outZ, uint8_t* outFlags, uint32_t* outIters) {
+  const int n = d->n, mX = d->s[0].m, mZ = d->s[1].m;
+  const size_t in_bytes = ((size_t)(mX + mZ) * nf + 15) / 16 * 16;
+  const size_t it_off = in_bytes, x_off = it_off + (size_t)8 * nf, z_off = x_off + (size_t)n * nf,
+               f_off = z_off + (size_t)n * nf, total = (f_off + nf + 15) / 16 * 16;
+  if (total > d->small_pin_bytes) {
+    if (d->small_pin) cudaFreeHost(d->small_pin);
+    d->small_pin = nullptr;
+    d->small_pin_bytes = 0;
+    const size_t want = std::max<size_t>(total, (size_t)64 << 10);
+    CU_TRY(cudaMallocHost((void**)&d->small_pin, want));
+    d->small_pin_bytes = want;
+  }
+  int rc = ensure_stage(d, total);
+  if (rc) return rc;
+  uint8_t* h = d->small_pin;
+  uint8_t* g = (uint8_t*)d->stage;
+  std::memcpy(h, synX, (size_t)mX * nf);
+  std::memcpy(h + (size_t)mX * nf, synZ, (size_t)mZ * nf);
+  auto enqueue = [&]() -> int {
+    CU_TRY(cudaMemcpyAsync(g, h, (size_t)(mX + mZ) * nf, cudaMemcpyHostToDevice, d->stream));
+    {
+      Timed t(d, QLDPC_T_PACK);
+      CU_TRY(launch_pack2(g, mX, d->s[0].mw, d->synX, g + (size_t)mX * nf, mZ, d->s[1].mw, d->synZ, nf, d->stream));
+    }
+    int r = run_bp(d, d->synX, d->synZ, nf, errorProbability, maxIterations, d->decX, d->decZ, d->sfX, d->sfZ, d->itX, d->itZ);
+    if (r) return r;
+    {
+      Timed t(d, QLDPC_T_PACK);
+      CU_TRY(launch_finish_small(d->decX, d->decZ, nf, n, d->nw, g + x_off, g + z_off, d->sfX, d->sfZ, g + f_off, d->itX,
+                                 d->itZ, (uint32_t*)(g + it_off), d->stream));
+    }
+    CU_TRY(cudaMemcpyAsync(h + it_off, g + it_off, f_off + nf - it_off, cudaMemcpyDeviceToHost, d->stream));
+    return QLDPC_OK;
+  };
+  // Graph replay: valid while the shape (frames, prior, iteration limit), the staging buffers and the launch
+  // configuration are those of the captured call.  Not used with per-kernel timing (its events are host-recorded) or
+  // on the HBM-resident path (host-polled passes).
+  uint32_t p_bits;
+  std::memcpy(&p_bits, &errorProbability, 4);
+  const bool graphable = !d->timing && !d->s[0].use_global && !d->s[1].use_global && ensure_side_stream(d) == QLDPC_OK;
+  qldpc_decoder::SmallGraph& sg = d->small_graph;
+  if (graphable && sg.exec && sg.nf == nf && sg.maxit == maxIterations && sg.p_bits == p_bits && sg.stage == g &&
+      sg.pin == h && sg.cfg_epoch == d->cfg_epoch) {
+    CU_TRY(cudaGraphLaunch(sg.exec, d->stream));
+    d->launches[QLDPC_T_PACK] += 2;  // the replayed graph holds the same four kernels the capture counted
+    d->launches[QLDPC_T_BP_X] += 1;
+    d->launches[QLDPC_T_BP_Z] += 1;
+  } else if (graphable) {
+    if (sg.exec) cudaGraphExecDestroy(sg.exec);
+    sg.exec = nullptr;
+    cudaGraph_t graph = nullptr;
+    CU_TRY(cudaStreamBeginCapture(d->stream, cudaStreamCaptureModeThreadLocal));
+    rc = enqueue();
+    const cudaError_t ce = cudaStreamEndCapture(d->stream, &graph);
+    if (rc || ce != cudaSuccess) {
+      if (graph) cudaGraphDestroy(graph);
+      cudaGetLastError();
+      if (rc) return rc;
+      rc = enqueue();  // capture refused (e.g. a legacy-stream interaction): plain stream operations
+      if (rc) return rc;
+    } else {
+      const cudaError_t ie = cudaGraphInstantiate(&sg.exec, graph, 0);
+      cudaGraphDestroy(graph);
+      if (ie != cudaSuccess) {
+        cudaGetLastError();
+        sg.exec = nullptr;
+        rc = enqueue();
+        if (rc) return rc;
+      } else {
+        sg.nf = nf; sg.maxit = maxIterations; sg.p_bits = p_bits; sg.stage = g; sg.pin = h; sg.cfg_epoch = d->cfg_epoch;
+        CU_TRY(cudaGraphLaunch(sg.exec, d->stream));
+      }
+    }
+  } else {
+    rc = enqueue();
+    if (rc) return rc;
+  }
+  CU_TRY(cudaStreamSynchronize(d->stream));
+  std::memcpy(outX, h + x_off, (size_t)n * nf);
+  std::memcpy(outZ, h + z_off, (size_t)n * nf);
+  std::memcpy(outFlags, h + f_off, (size_t)nf);
+  if (outIters) std::memcpy(outIters, h + it_off, (size_t)8 * nf);
+  return QLDPC_OK;
+}
+
+static int decode_batch_impl(qldpc_decoder* dec, const uint8_t* synX, const uint8_t* synZ, int64_t nframes,
+                             float errorProbability, int maxIterations, uint8_t* outX, uint8_t* outZ, uint8_t* outFlags,
+                             uint32_t* outIters);
+
 int qldpc_decode_batch(qldpc_decoder* dec, const uint8_t* synX, const uint8_t* synZ, int64_t nframes,
                        float errorProbability, int maxIterations, uint8_t* outX, uint8_t* outZ, uint8_t* outFlags,
                        uint32_t* outIters) {
   int rc = check_common(dec, nframes, maxIterations);
   if (rc) return rc;
   if (!synX || !synZ || !outX || !outZ || !outFlags) return fail(QLDPC_ERR_ARG, "null buffer");
+  if (nframes == 0) return QLDPC_OK;
+  if (nframes <= std::min<int64_t>(kSmallBatch, dec->chunk))
+    rc = decode_small(dec, synX, synZ, (int)nframes, errorProbability, maxIterations, outX, outZ, outFlags, outIters);
+  else
+    rc = decode_batch_impl(dec, synX, synZ, nframes, errorProbability, maxIterations, outX, outZ, outFlags, outIters);
+  if (rc) {
+    const std::string keep = g_err;
+    quiesce(dec);
+    g_err = keep;
+  }
+  return rc;
+}
+
+static int decode_batch_impl(qldpc_decoder* dec, const uint8_t* synX, const uint8_t* synZ, int64_t nframes,
+                             float errorProbability, int maxIterations, uint8_t* outX, uint8_t* outZ, uint8_t* outFlags,
+                             uint32_t* outIters) {
+  int rc = QLDPC_OK;
   // Three-stage pipeline over slices of at most kPipeFrames frames, two staging buffers per direction:
   //   copy stream : H2D of slice i+1          (waits until slice i-1 has been packed out of that buffer)
   //   main stream : pack, BP X/Z, unpack, flags of slice i   (waits until slice i-2 has left the output buffer)
@@ -749,16 +951,18 @@ int qldpc_decode_batch(qldpc_decoder* dec, const uint8_t* synX, const uint8_t* s
     rc = ensure_pipeline(d);
     if (rc) return rc;
     const size_t dev_stride = (dev_one + 15) / 16 * 16;
+    std::vector<int64_t> starts;  // first frame of every slice issued so far
     auto unpack_slice = [&](int j) {  // corrections of slice j: pinned words -> the caller's byte rows
-      const int64_t o = (int64_t)j * slice;
-      const int cnt = (int)std::min<int64_t>(slice, nframes - o);
+      const int64_t o = starts[(size_t)j];
+      const int cnt = (int)std::min<int64_t>(slice_frames(j, slice), nframes - o);
       const uint32_t* hout = d->pin + 2 * in_w + (size_t)(j & 1) * out_w;
       hp->unpack(hout, cnt, n, nw, outX + o * n);
       hp->unpack(hout + (size_t)cnt * nw, cnt, n, nw, outZ + o * n);
     };
     int i = 0;
-    for (int64_t off = 0; off < nframes; off += slice, ++i) {
-      const int nf = (int)std::min<int64_t>(slice, nframes - off);
+    for (int64_t off = 0; off < nframes; off += slice_frames(i, slice), ++i) {
+      const int nf = (int)std::min<int64_t>(slice_frames(i, slice), nframes - off);
+      starts.push_back(off);
       const int b = i & 1;
       uint32_t* hin = d->pin + (size_t)b * in_w;
       uint32_t* hout = d->pin + 2 * in_w + (size_t)b * out_w;
@@ -815,8 +1019,8 @@ int qldpc_decode_batch(qldpc_decoder* dec, const uint8_t* synX, const uint8_t* s
   rc = ensure_pipeline(d);
   if (rc) return rc;
   int i = 0;
-  for (int64_t off = 0; off < nframes; off += slice, ++i) {
-    const int nf = (int)std::min<int64_t>(slice, nframes - off);
+  for (int64_t off = 0; off < nframes; off += slice_frames(i, slice), ++i) {
+    const int nf = (int)std::min<int64_t>(slice_frames(i, slice), nframes - off);
     const int b = i & 1;
     uint8_t* base = (uint8_t*)d->stage + (size_t)b * one;
     uint32_t* its = (uint32_t*)base;          // [nf][2], kept first for alignment
@@ -874,11 +1078,7 @@ int qldpc_get_statistics_depolarizing(qldpc_decoder* dec, uint64_t seed, uint64_
   CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
   for (int64_t off = 0; off < nframes; off += d->chunk) {
     const int nf = (int)std::min<int64_t>(d->chunk, nframes - off);
-    {
-      Timed t(d, QLDPC_T_GENERATE);
-      CU_TRY(launch_generate(seed, first_frame + (uint64_t)off, nf, d->n, d->nw, thr, d->errX, d->errZ, d->stream));
-    }
-    rc = run_syndrome(d, nf);
+    rc = run_generate(d, seed, first_frame + (uint64_t)off, nf, thr);
     if (rc) return rc;
     rc = finish_chunk(d, nf, off, p, maxIterations, perFrameFlags, perFrameIters);
     if (rc) return rc;
@@ -889,9 +1089,24 @@ int qldpc_get_statistics_depolarizing(qldpc_decoder* dec, uint64_t seed, uint64_
 // GetStatistics(errorWeight, numErrors, ...) (DecoderCPU.h:392-530): the reference's fixed-weight generator
 // (WeightWGenerator, host_pack.h: one serial mt19937 stream, as published) feeding the device decoder.  Slices are
 // generated into two pinned buffers while the device decodes the previous slice.
+static int weightw_impl(qldpc_decoder* dec, int errorWeight, int64_t numErrors, float errorProbability, int maxIterations,
+                        uint32_t seed, uint64_t* counters, uint8_t* perFrameFlags, uint32_t* perFrameIters);
+
 int qldpc_get_statistics_weightw(qldpc_decoder* dec, int errorWeight, int64_t numErrors, float errorProbability,
                                  int maxIterations, uint32_t seed, uint64_t* counters, uint8_t* perFrameFlags,
                                  uint32_t* perFrameIters) {
+  const int rc = weightw_impl(dec, errorWeight, numErrors, errorProbability, maxIterations, seed, counters, perFrameFlags,
+                              perFrameIters);
+  if (rc && dec) {
+    const std::string keep = g_err;
+    quiesce(dec);
+    g_err = keep;
+  }
+  return rc;
+}
+
+static int weightw_impl(qldpc_decoder* dec, int errorWeight, int64_t numErrors, float errorProbability, int maxIterations,
+                        uint32_t seed, uint64_t* counters, uint8_t* perFrameFlags, uint32_t* perFrameIters) {
   int rc = check_common(dec, numErrors, maxIterations);
   if (rc) return rc;
   if (errorWeight < 0) return fail(QLDPC_ERR_ARG, "negative error weight");
@@ -935,9 +1150,26 @@ int qldpc_get_statistics_weightw(qldpc_decoder* dec, int errorWeight, int64_t nu
 // Host-supplied error patterns are processed in slices of at most kPipeFrames frames: slice i+1 is copied to the device
 // on a second stream while slice i is packed, decoded and reduced (two staging buffers, events for hand-over), so
 // with pinned host memory the PCIe transfer hides behind the decode (or vice versa).
+static int stats_from_errors_impl(qldpc_decoder* d, const void* xErrors, const void* zErrors, int elem, int64_t numErrors,
+                                  float errorProbability, int maxIterations, uint64_t* counters, uint8_t* perFrameFlags,
+                                  uint32_t* perFrameIters);
+
 static int stats_from_errors(qldpc_decoder* d, const void* xErrors, const void* zErrors, int elem, int64_t numErrors,
                              float errorProbability, int maxIterations, uint64_t* counters, uint8_t* perFrameFlags,
                              uint32_t* perFrameIters) {
+  const int rc = stats_from_errors_impl(d, xErrors, zErrors, elem, numErrors, errorProbability, maxIterations, counters,
+                                        perFrameFlags, perFrameIters);
+  if (rc && d) {
+    const std::string keep = g_err;
+    quiesce(d);
+    g_err = keep;
+  }
+  return rc;
+}
+
+static int stats_from_errors_impl(qldpc_decoder* d, const void* xErrors, const void* zErrors, int elem, int64_t numErrors,
+                                  float errorProbability, int maxIterations, uint64_t* counters, uint8_t* perFrameFlags,
+                                  uint32_t* perFrameIters) {
   int rc = check_common(d, numErrors, maxIterations);
   if (rc) return rc;
   if (!xErrors || !zErrors) return fail(QLDPC_ERR_ARG, "null buffer");
@@ -957,8 +1189,8 @@ static int stats_from_errors(qldpc_decoder* d, const void* xErrors, const void* 
     if (rc) return rc;
     CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
     int i = 0;
-    for (int64_t off = 0; off < numErrors; off += slice, ++i) {
-      const int nf = (int)std::min<int64_t>(slice, numErrors - off);
+    for (int64_t off = 0; off < numErrors; off += slice_frames(i, slice), ++i) {
+      const int nf = (int)std::min<int64_t>(slice_frames(i, slice), numErrors - off);
       const int b = i & 1;
       uint32_t* hbuf = d->pin + (size_t)b * hwords;
       uint32_t* dbuf = (uint32_t*)d->stage + (size_t)b * hwords;
@@ -987,8 +1219,8 @@ static int stats_from_errors(qldpc_decoder* d, const void* xErrors, const void* 
   if (rc) return rc;
   CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
   int i = 0;
-  for (int64_t off = 0; off < numErrors; off += slice, ++i) {
-    const int nf = (int)std::min<int64_t>(slice, numErrors - off);
+  for (int64_t off = 0; off < numErrors; off += slice_frames(i, slice), ++i) {
+    const int nf = (int)std::min<int64_t>(slice_frames(i, slice), numErrors - off);
     const int b = i & 1;
     uint8_t* st0 = (uint8_t*)d->stage + (size_t)b * half;
     uint8_t* st1 = st0 + row * nf;
@@ -1049,6 +1281,22 @@ int qldpc_debug_host_pack(const void* src, int elem_size, int64_t rows, int cols
   return QLDPC_OK;
 }
 
+int qldpc_debug_host_read_gbs(const void* src, int64_t bytes, int threads, int repeats, double* gbs) {
+  if (!src || bytes < 1 || threads < 1 || threads > 64 || repeats < 1 || !gbs) return fail(QLDPC_ERR_ARG, "bad argument");
+  HostPacker hp(threads);
+  volatile uint64_t sink = hp.read_all(src, (size_t)bytes);  // first pass: page in, wake the workers
+  double best = 0.0;
+  for (int r = 0; r < repeats; ++r) {
+    const auto t0 = std::chrono::steady_clock::now();
+    sink = sink | hp.read_all(src, (size_t)bytes);
+    const double sec = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+    best = std::max(best, (double)bytes / sec / 1e9);
+  }
+  (void)sink;
+  *gbs = best;
+  return QLDPC_OK;
+}
+
 int qldpc_debug_host_unpack(const uint32_t* src, int64_t rows, int cols, uint8_t* dst, int threads) {
   if (!src || !dst || rows < 0 || cols < 1 || threads < 1 || threads > 64) return fail(QLDPC_ERR_ARG, "bad argument");
   HostPacker hp(threads);
@@ -1069,8 +1317,7 @@ int qldpc_debug_generate(qldpc_decoder* dec, uint64_t seed, uint64_t first_frame
   const Thresholds thr = depolarizing_thresholds(p);
   for (int64_t off = 0; off < nframes; off += d->chunk) {
     const int nf = (int)std::min<int64_t>(d->chunk, nframes - off);
-    CU_TRY(launch_generate(seed, first_frame + (uint64_t)off, nf, n, d->nw, thr, d->errX, d->errZ, d->stream));
-    rc = run_syndrome(d, nf);
+    rc = run_generate(d, seed, first_frame + (uint64_t)off, nf, thr);
     if (rc) return rc;
     struct { const uint32_t* src; int cols, words; uint8_t* dst; } jobs[4] = {
         {d->errX, n, d->nw, xerr}, {d->errZ, n, d->nw, zerr}, {d->synX, mX, d->s[0].mw, synX}, {d->synZ, mZ, d->s[1].mw, synZ}};

@@ -1,5 +1,6 @@
-// See host_pack.h.  The inner loops have an AVX2 form (32 source elements per step), selected at run time, and a
-// portable form; both produce the same words.
+// See host_pack.h.  The inner loops have an AVX-512 form (vptestmd / vptestmb straight into mask registers, software
+// prefetch ahead of the stream), an AVX2 form (32 source elements per step) and a portable form, selected at run time;
+// all produce the same words.
 #include "host_pack.h"
 
 #include <algorithm>
@@ -31,9 +32,10 @@ int default_host_threads() {
       if (local > 1) hw = std::max(1u, hw / (unsigned)local);
       break;
     }
-  // packing needs ~8 threads to outrun the raw copy over the link (profiles/r1_bench_host_pack.jsonl); with fewer
-  // cores to itself a process copies the raw rows instead
-  return hw < 6 ? 0 : (int)std::min(16u, hw);
+  // Always pack on the host: the packed rows are 1/32 (int) or 1/8 (byte) of the bytes, and the source buffers then
+  // cross the host memory bus once instead of once for the DMA engine; with few cores per process (8 ranks on a
+  // 32-core box) the call is bound by host memory bandwidth either way (bench.py reports that roofline).
+  return (int)std::max(1u, std::min(16u, hw));
 }
 
 // ----------------------------------------------------------------------------------------------- row kernels
@@ -81,6 +83,54 @@ __attribute__((target("avx2"))) static void pack_rows_avx2_u8(const uint8_t* src
   }
 }
 
+// AVX-512: 16 ints (or 64 bytes) per test instruction, result lands in a mask register.  The loads are ordinary
+// (write-back memory: a non-temporal load is only a hint there); a software prefetch a few lines ahead keeps more
+// requests in flight per core than the hardware prefetcher alone, which is what a memory-bound single thread needs.
+__attribute__((target("avx512f,avx512bw"))) static void pack_rows_avx512_i32(const int32_t* src, int64_t r0, int64_t r1,
+                                                                             int cols, int words, uint32_t* dst) {
+  const int full = cols / 32;
+  for (int64_t r = r0; r < r1; ++r) {
+    const int32_t* p = src + r * cols;
+    uint32_t* d = dst + r * words;
+    for (int w = 0; w < full; ++w, p += 32) {
+      _mm_prefetch(reinterpret_cast<const char*>(p) + 1536, _MM_HINT_NTA);
+      _mm_prefetch(reinterpret_cast<const char*>(p) + 1600, _MM_HINT_NTA);
+      const __m512i a = _mm512_loadu_si512(p), b = _mm512_loadu_si512(p + 16);
+      d[w] = (uint32_t)_mm512_test_epi32_mask(a, a) | ((uint32_t)_mm512_test_epi32_mask(b, b) << 16);
+    }
+    for (int w = full; w < words; ++w, p += 32) d[w] = word_portable(p, std::max(0, std::min(32, cols - 32 * w)));
+  }
+}
+
+__attribute__((target("avx512f,avx512bw"))) static void pack_rows_avx512_u8(const uint8_t* src, int64_t r0, int64_t r1,
+                                                                            int cols, int words, uint32_t* dst) {
+  const int full = cols / 64;  // two words per step
+  for (int64_t r = r0; r < r1; ++r) {
+    const uint8_t* p = src + r * cols;
+    uint32_t* d = dst + r * words;
+    int w = 0;
+    for (int k = 0; k < full; ++k, p += 64, w += 2) {
+      _mm_prefetch(reinterpret_cast<const char*>(p) + 1024, _MM_HINT_NTA);
+      const __m512i a = _mm512_loadu_si512(p);
+      const uint64_t m = (uint64_t)_mm512_test_epi8_mask(a, a);
+      d[w] = (uint32_t)m;
+      d[w + 1] = (uint32_t)(m >> 32);
+    }
+    for (; w < words; ++w, p += 32) d[w] = word_portable(p, std::max(0, std::min(32, cols - 32 * w)));
+  }
+}
+
+// streaming read of `bytes` bytes (the packers' access pattern without their arithmetic): the host-memory roofline probe
+__attribute__((target("avx512f,avx512bw"))) static uint64_t read_avx512(const uint8_t* p, size_t bytes) {
+  __m512i acc = _mm512_setzero_si512();
+  size_t i = 0;
+  for (; i + 64 <= bytes; i += 64) {
+    _mm_prefetch(reinterpret_cast<const char*>(p + i) + 1536, _MM_HINT_NTA);
+    acc = _mm512_or_si512(acc, _mm512_loadu_si512(p + i));
+  }
+  return (uint64_t)_mm512_reduce_or_epi64(acc);
+}
+
 // one byte per bit from packed words: 8 bits -> 8 bytes through a 64-bit multiply-free spread
 __attribute__((target("avx2"))) static void unpack_rows_avx2(const uint32_t* src, int64_t r0, int64_t r1, int cols,
                                                              int words, uint8_t* dst) {
@@ -117,6 +167,15 @@ static void unpack_rows_portable(const uint32_t* src, int64_t r0, int64_t r1, in
     uint8_t* d = dst + r * cols;
     for (int c = 0; c < cols; ++c) d[c] = (uint8_t)((s[c >> 5] >> (c & 31)) & 1u);
   }
+}
+
+static bool have_avx512() {
+#ifdef QLDPC_X86
+  static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+  return ok;
+#else
+  return false;
+#endif
 }
 
 static bool have_avx2() {
@@ -179,11 +238,16 @@ void HostPacker::run(const std::function<void(int)>& job) {
 
 void HostPacker::pack(const void* src, int elem, int64_t rows, int cols, int words, uint32_t* dst) {
   if (rows <= 0) return;
-  const bool avx2 = have_avx2();
+  const bool avx2 = have_avx2(), avx512 = have_avx512();
   const int T = nthreads_;
   run([&](int id) {
     const int64_t r0 = rows * id / T, r1 = rows * (id + 1) / T;
 #ifdef QLDPC_X86
+    if (avx512) {
+      if (elem == 4) pack_rows_avx512_i32((const int32_t*)src, r0, r1, cols, words, dst);
+      else pack_rows_avx512_u8((const uint8_t*)src, r0, r1, cols, words, dst);
+      return;
+    }
     if (avx2) {
       if (elem == 4) pack_rows_avx2_i32((const int32_t*)src, r0, r1, cols, words, dst);
       else pack_rows_avx2_u8((const uint8_t*)src, r0, r1, cols, words, dst);
@@ -193,6 +257,32 @@ void HostPacker::pack(const void* src, int elem, int64_t rows, int cols, int wor
     if (elem == 4) pack_rows_portable((const int32_t*)src, r0, r1, cols, words, dst);
     else pack_rows_portable((const uint8_t*)src, r0, r1, cols, words, dst);
   });
+}
+
+uint64_t HostPacker::read_all(const void* src, size_t bytes) {
+  std::vector<uint64_t> part((size_t)nthreads_, 0);
+  const int T = nthreads_;
+  const bool avx512 = have_avx512();
+  run([&](int id) {
+    const size_t b0 = bytes / 64 * id / T * 64, b1 = id == T - 1 ? bytes : bytes / 64 * (id + 1) / T * 64;
+    const uint8_t* p = (const uint8_t*)src + b0;
+    uint64_t acc = 0;
+#ifdef QLDPC_X86
+    if (avx512) {
+      part[(size_t)id] = read_avx512(p, b1 - b0);
+      return;
+    }
+#endif
+    for (size_t i = 0; i + 8 <= b1 - b0; i += 8) {
+      uint64_t v;
+      std::memcpy(&v, p + i, 8);
+      acc |= v;
+    }
+    part[(size_t)id] = acc;
+  });
+  uint64_t acc = 0;
+  for (uint64_t v : part) acc |= v;
+  return acc;
 }
 
 void HostPacker::unpack(const uint32_t* src, int64_t rows, int cols, int words, uint8_t* dst) {

@@ -22,6 +22,9 @@ class HostPacker {
   void pack(const void* src, int elem, int64_t rows, int cols, int words, uint32_t* dst);
   // dst[r * cols + c] = bit c of src[r * words ..] as one byte
   void unpack(const uint32_t* src, int64_t rows, int cols, int words, uint8_t* dst);
+  // streaming read of a host buffer by all threads (OR of its words): the memory-bandwidth probe behind bench.py's
+  // host_mem_roofline
+  uint64_t read_all(const void* src, size_t bytes);
   // runs job(id) for id = 0 .. threads()-1, id 0 on the calling thread; returns when all are done
   void parallel(const std::function<void(int)>& job) { run(job); }
 
@@ -63,7 +66,7 @@ class WeightWGenerator {
   std::vector<uint32_t> draws_;
 };
 
-// default worker count: QLDPC_HOST_THREADS if set, else min(16, hardware threads / local ranks), 0 if that is below 6
+// default worker count: QLDPC_HOST_THREADS if set, else min(16, hardware threads / local ranks), at least 1
 int default_host_threads();
 
 }  // namespace qldpc

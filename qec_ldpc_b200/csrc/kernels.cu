@@ -4,6 +4,7 @@
 
 #include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 
 #include "../../include/qldpc_b200.h"
 
@@ -15,13 +16,34 @@ namespace qldpc {
 
 typedef void (*BpKernel)(const BpArgs);
 constexpr int kMaxT = 512;
+
+// Multiprocessor count of the current device (grids of the grid-stride kernels are sized in multiples of it).
+static int sm_count() {
+  static thread_local int cached_dev = -1, cached = 0;
+  int dev = 0;
+  cudaGetDevice(&dev);
+  if (dev != cached_dev) {
+    int v = 0;
+    cached = cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0 ? v : 148;
+    cached_dev = dev;
+  }
+  return cached;
+}
 // one translation unit per shape (bp_shape_<dc>_<dv>.cu)
 #define QLDPC_SHAPES(X) X(6, 3) X(10, 4) X(10, 5) X(8, 4) X(8, 3) X(12, 6) X(10, 3) X(12, 3) X(12, 4) X(12, 5) X(4, 2) X(6, 2) X(8, 2) X(10, 2) X(12, 2)
 #define QLDPC_DECL(DC, DV) BpKernel bp_shape_##DC##_##DV(int vec, int guard, int m);
 QLDPC_SHAPES(QLDPC_DECL)
 #undef QLDPC_DECL
 
+// QLDPC_NO_SPECIALIZE=1 in the environment forces the generic kernels (check count as a run-time value) even where an
+// instantiation with a compile-time check count exists; the parity tests run both.
+static bool specialization_enabled() {
+  const char* e = getenv("QLDPC_NO_SPECIALIZE");
+  return !(e && e[0] && e[0] != '0');
+}
+
 static BpKernel lookup_kernel(int dc, int dv, int vec, int guard, int m) {
+  if (!specialization_enabled()) m = 0;
 #define QLDPC_CASE(DC, DV) \
   if (dc == DC && dv == DV) return bp_shape_##DC##_##DV(vec, guard, m);
   QLDPC_SHAPES(QLDPC_CASE)
@@ -132,19 +154,68 @@ cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, i
 }
 
 // =====================================================================================================
-// Error generation: device-side counter-based Philox depolarizing noise (replaces the mt19937 weight-W
-// generator of DecoderCPU.h:394-396,446-459 / RandomErrorGenerator.h:31-44 for the Monte-Carlo path).
-// One warp per frame; lane b handles Philox block b (qubits 4b..4b+3); eight lanes assemble one 32-bit word.
+// Error generation + syndrome in one kernel: device-side counter-based Philox depolarizing noise (replaces the
+// mt19937 weight-W generator of DecoderCPU.h:394-396,446-459 / RandomErrorGenerator.h:31-44 for the Monte-Carlo path)
+// and s = H e (mod 2) of both sides (Quantum_LDPC_Code::GetSyndromeX/Z, Quantum_LDPC_Code.h:94-124) -- the reference's
+// intended "generate syndrome" step of its statistics kernel (kernels.cu:252-268).  One warp per frame; lane b handles
+// Philox block b (qubits 4b..4b+3): the erroneous qubits flip their dv checks in the warp's shared-memory syndrome
+// words straight from the registers that hold the fresh error bits, so the errors are written to HBM once (the
+// statistics kernel needs them) and never read back; eight lanes assemble one 32-bit error word.
 // =====================================================================================================
-__global__ void __launch_bounds__(256) generate_kernel(uint64_t seed, uint64_t first_frame, int nframes, int n, int nw,
-                                                       Thresholds thr, uint32_t* __restrict__ errX,
-                                                       uint32_t* __restrict__ errZ) {
-  const int lane = threadIdx.x & 31;
+// Syndrome of one side from the frame's error words in shared memory: the positions of the set bits are compacted into
+// a list (warp prefix sum of the word popcounts), then the (error, k-th check of its variable) pairs are dealt out
+// evenly over the 32 lanes, so the scatter runs without lane divergence however the errors cluster.
+__device__ __forceinline__ void scatter_side(const uint32_t* errw, int nw, uint16_t* list, const uint16_t* __restrict__ vchk,
+                                             int n, int dv, uint32_t* syn, int lane) {
+  int count = 0;
+  for (int w0 = 0; w0 < nw; w0 += 32) {
+    const int w = w0 + lane;
+    uint32_t word = w < nw ? errw[w] : 0u;
+    const int c = __popc(word);
+    int incl = c;
+#pragma unroll
+    for (int s = 1; s < 32; s <<= 1) {
+      const int t = __shfl_up_sync(0xffffffffu, incl, s);
+      if (lane >= s) incl += t;
+    }
+    int pos = count + incl - c;
+    while (word) {
+      list[pos++] = (uint16_t)(w * 32 + __ffs((int)word) - 1);
+      word &= word - 1u;
+    }
+    count += __shfl_sync(0xffffffffu, incl, 31);
+  }
+  __syncwarp();
+  const int items = count * dv;
+  for (int i = lane; i < items; i += 32) {
+    const int j = i / dv, k = i - j * dv;
+    const int e = vchk[k * n + list[j]];
+    atomicXor(&syn[e >> 5], 1u << (e & 31));
+  }
+}
+
+__global__ void __launch_bounds__(256) generate_syndrome_kernel(uint64_t seed, uint64_t first_frame, int nframes, int n,
+                                                                int nw, Thresholds thr, uint32_t* __restrict__ errX,
+                                                                uint32_t* __restrict__ errZ,
+                                                                const uint16_t* __restrict__ vchkX, int dvX, int mwX,
+                                                                uint32_t* __restrict__ synX,
+                                                                const uint16_t* __restrict__ vchkZ, int dvZ, int mwZ,
+                                                                uint32_t* __restrict__ synZ) {
+  extern __shared__ uint32_t sh[];
+  const int lane = threadIdx.x & 31, wib = threadIdx.x >> 5;
   const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   const int nwarps = (gridDim.x * blockDim.x) >> 5;
   const int nblocks = (n + 3) >> 2;
+  // per warp: error words x, z [nw each], syndrome words [mwX + mwZ], position list [n] (16-bit)
+  const int per_warp = 2 * nw + mwX + mwZ + (n + 1) / 2;
+  uint32_t* ex = sh + (size_t)wib * per_warp;
+  uint32_t* ez = ex + nw;
+  uint32_t* smX = ez + nw;
+  uint32_t* smZ = smX + mwX;
+  uint16_t* list = reinterpret_cast<uint16_t*>(smZ + mwZ);
   for (int f = warp; f < nframes; f += nwarps) {
     const uint64_t frame = first_frame + (uint64_t)f;
+    for (int w = lane; w < mwX + mwZ; w += 32) smX[w] = 0u;
     for (int b0 = 0; b0 < nblocks; b0 += 32) {
       const int b = b0 + lane;
       uint32_t xn = 0, zn = 0;
@@ -167,16 +238,34 @@ __global__ void __launch_bounds__(256) generate_kernel(uint64_t seed, uint64_t f
       if ((lane & 7) == 0 && w < nw) {
         errX[(size_t)f * nw + w] = xv;
         errZ[(size_t)f * nw + w] = zv;
+        ex[w] = xv;
+        ez[w] = zv;
       }
     }
+    __syncwarp();
+    if (synX) {
+      scatter_side(ex, nw, list, vchkX, n, dvX, smX, lane);
+      __syncwarp();
+      scatter_side(ez, nw, list, vchkZ, n, dvZ, smZ, lane);
+      __syncwarp();
+      for (int w = lane; w < mwX; w += 32) synX[(size_t)f * mwX + w] = smX[w];
+      for (int w = lane; w < mwZ; w += 32) synZ[(size_t)f * mwZ + w] = smZ[w];
+    }
+    __syncwarp();
   }
 }
 
-cudaError_t launch_generate(uint64_t seed, uint64_t first_frame, int nframes, int n, int nw, Thresholds thr,
-                            uint32_t* errX, uint32_t* errZ, cudaStream_t st) {
+cudaError_t launch_generate_syndrome(uint64_t seed, uint64_t first_frame, int nframes, int n, int nw, Thresholds thr,
+                                     uint32_t* errX, uint32_t* errZ, const uint16_t* vchkX, int dvX, int mwX,
+                                     uint32_t* synX, const uint16_t* vchkZ, int dvZ, int mwZ, uint32_t* synZ,
+                                     cudaStream_t st) {
   if (nframes <= 0) return cudaSuccess;
-  const int blocks = std::min((nframes + 7) / 8, 148 * 16);
-  generate_kernel<<<blocks, 256, 0, st>>>(seed, first_frame, nframes, n, nw, thr, errX, errZ);
+  const size_t per_warp = (size_t)(2 * nw + mwX + mwZ + (n + 1) / 2) * sizeof(uint32_t);
+  if (per_warp > 48 * 1024) return cudaErrorInvalidValue;
+  const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / per_warp));
+  const int blocks = std::min((nframes + warps - 1) / warps, sm_count() * 16);
+  generate_syndrome_kernel<<<blocks, 32 * warps, warps * per_warp, st>>>(seed, first_frame, nframes, n, nw, thr, errX, errZ,
+                                                                       vchkX, dvX, mwX, synX, vchkZ, dvZ, mwZ, synZ);
   return cudaGetLastError();
 }
 
@@ -228,7 +317,7 @@ cudaError_t launch_syndrome(const uint32_t* errX, const uint32_t* errZ, int nfra
   // one warp per frame with max(mwX, mwZ) words of shared memory each; fewer warps per block for very wide codes
   const size_t per_warp = (size_t)std::max(mwX, mwZ) * sizeof(uint32_t);
   const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, (48 * 1024) / per_warp));
-  const int blocks = std::min((nframes + warps - 1) / warps, 148 * 16);
+  const int blocks = std::min((nframes + warps - 1) / warps, sm_count() * 16);
   syndrome_kernel<<<blocks, 32 * warps, warps * per_warp, st>>>(errX, errZ, nframes, n, nw, vchkX, dvX, mwX, synX, vchkZ,
                                                                dvZ, mwZ, synZ);
   return cudaGetLastError();
@@ -266,7 +355,7 @@ __global__ void __launch_bounds__(256) unpack_kernel(const uint32_t* __restrict_
 
 cudaError_t launch_pack(const void* src, int elem_size, int64_t rows, int cols, int words, uint32_t* dst, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  const int blocks = (int)std::min<int64_t>((rows * words + 7) / 8, 148 * 32);
+  const int blocks = (int)std::min<int64_t>((rows * words + 7) / 8, sm_count() * 32);
   if (elem_size == 1) pack_kernel<uint8_t><<<blocks, 256, 0, st>>>((const uint8_t*)src, rows, cols, words, dst);
   else pack_kernel<int32_t><<<blocks, 256, 0, st>>>((const int32_t*)src, rows, cols, words, dst);
   return cudaGetLastError();
@@ -274,8 +363,66 @@ cudaError_t launch_pack(const void* src, int elem_size, int64_t rows, int cols, 
 
 cudaError_t launch_unpack(const uint32_t* src, int64_t rows, int cols, int words, uint8_t* dst, cudaStream_t st) {
   if (rows <= 0) return cudaSuccess;
-  const int blocks = (int)std::min<int64_t>((rows * cols + 255) / 256, 148 * 32);
+  const int blocks = (int)std::min<int64_t>((rows * cols + 255) / 256, sm_count() * 32);
   unpack_kernel<<<blocks, 256, 0, st>>>(src, rows, cols, words, dst);
+  return cudaGetLastError();
+}
+
+// Small-batch helpers of the low-latency Decode path: both syndrome rows packed by one launch, and everything a
+// frame returns (corrections of both sides as bytes, ErrorCode bits, iteration counts) produced by one launch.
+__global__ void __launch_bounds__(256) pack2_kernel(const uint8_t* __restrict__ srcX, int colsX, int wordsX,
+                                                    uint32_t* __restrict__ dstX, const uint8_t* __restrict__ srcZ,
+                                                    int colsZ, int wordsZ, uint32_t* __restrict__ dstZ, int rows) {
+  const int lane = threadIdx.x & 31;
+  const int warp = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const int nwarps = (gridDim.x * blockDim.x) >> 5;
+  const int per = wordsX + wordsZ, total = rows * per;
+  for (int t = warp; t < total; t += nwarps) {
+    const int r = t / per, w = t - r * per;
+    const bool z = w >= wordsX;
+    const int ww = z ? w - wordsX : w, cols = z ? colsZ : colsX;
+    const uint8_t* src = z ? srcZ : srcX;
+    const int c = ww * 32 + lane;
+    const unsigned bit = c < cols ? (unsigned)(src[(size_t)r * cols + c] != 0) : 0u;
+    const unsigned word = __ballot_sync(0xffffffffu, bit);
+    if (lane == 0) (z ? dstZ : dstX)[(size_t)r * (z ? wordsZ : wordsX) + ww] = word;
+  }
+}
+
+cudaError_t launch_pack2(const uint8_t* srcX, int colsX, int wordsX, uint32_t* dstX, const uint8_t* srcZ, int colsZ,
+                         int wordsZ, uint32_t* dstZ, int rows, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  const int blocks = std::min((rows * (wordsX + wordsZ) + 7) / 8, sm_count() * 8);
+  pack2_kernel<<<blocks, 256, 0, st>>>(srcX, colsX, wordsX, dstX, srcZ, colsZ, wordsZ, dstZ, rows);
+  return cudaGetLastError();
+}
+
+__global__ void __launch_bounds__(256) finish_small_kernel(const uint32_t* __restrict__ decX,
+                                                           const uint32_t* __restrict__ decZ, int rows, int cols, int words,
+                                                           uint8_t* __restrict__ outX, uint8_t* __restrict__ outZ,
+                                                           const uint8_t* __restrict__ sfX, const uint8_t* __restrict__ sfZ,
+                                                           uint8_t* __restrict__ flags, const uint32_t* __restrict__ itX,
+                                                           const uint32_t* __restrict__ itZ, uint32_t* __restrict__ iters) {
+  const int total = rows * cols;
+  for (int t = blockIdx.x * blockDim.x + threadIdx.x; t < total; t += gridDim.x * blockDim.x) {
+    const int r = t / cols, c = t - r * cols;
+    outX[t] = (uint8_t)((decX[(size_t)r * words + (c >> 5)] >> (c & 31)) & 1u);
+    outZ[t] = (uint8_t)((decZ[(size_t)r * words + (c >> 5)] >> (c & 31)) & 1u);
+    if (c == 0) {
+      const unsigned sx = sfX[r], sz = sfZ[r];
+      flags[r] = (uint8_t)((sx & 1u) | ((sz & 1u) << 1) | (((sx >> 1) & 1u) << 2) | (((sz >> 1) & 1u) << 3));
+      iters[2 * r] = itX[r];
+      iters[2 * r + 1] = itZ[r];
+    }
+  }
+}
+
+cudaError_t launch_finish_small(const uint32_t* decX, const uint32_t* decZ, int rows, int cols, int words, uint8_t* outX,
+                                uint8_t* outZ, const uint8_t* sfX, const uint8_t* sfZ, uint8_t* flags, const uint32_t* itX,
+                                const uint32_t* itZ, uint32_t* iters, cudaStream_t st) {
+  if (rows <= 0) return cudaSuccess;
+  const int blocks = std::min((rows * cols + 255) / 256, sm_count() * 8);
+  finish_small_kernel<<<blocks, 256, 0, st>>>(decX, decZ, rows, cols, words, outX, outZ, sfX, sfZ, flags, itX, itZ, iters);
   return cudaGetLastError();
 }
 
@@ -375,7 +522,7 @@ cudaError_t launch_stats(const StatsArgs& a, cudaStream_t st) {
     if (e != cudaSuccess) return e;
   }
   const int warps = (int)std::max<size_t>(1, std::min<size_t>(8, cap / per_warp));
-  const int blocks = std::min((a.nframes + warps - 1) / warps, 148 * 8);
+  const int blocks = std::min((a.nframes + warps - 1) / warps, sm_count() * 8);
   stats_kernel<<<blocks, 32 * warps, warps * per_warp, st>>>(a);
   return cudaGetLastError();
 }
@@ -390,7 +537,7 @@ __global__ void __launch_bounds__(256) merge_flags_kernel(const uint8_t* __restr
 
 cudaError_t launch_merge_flags(const uint8_t* sfX, const uint8_t* sfZ, int nframes, uint8_t* out, cudaStream_t st) {
   if (nframes <= 0) return cudaSuccess;
-  merge_flags_kernel<<<std::min((nframes + 255) / 256, 148 * 8), 256, 0, st>>>(sfX, sfZ, nframes, out);
+  merge_flags_kernel<<<std::min((nframes + 255) / 256, sm_count() * 8), 256, 0, st>>>(sfX, sfZ, nframes, out);
   return cudaGetLastError();
 }
 
@@ -430,7 +577,7 @@ __global__ void __launch_bounds__(256) division_check_kernel(uint64_t seed, long
 }
 
 cudaError_t launch_division_check(uint64_t seed, long long npairs, unsigned long long* out, cudaStream_t st) {
-  division_check_kernel<<<148 * 8, 256, 0, st>>>(seed, npairs, out);
+  division_check_kernel<<<sm_count() * 8, 256, 0, st>>>(seed, npairs, out);
   return cudaGetLastError();
 }
 

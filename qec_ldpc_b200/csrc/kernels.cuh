@@ -38,9 +38,12 @@ size_t global_bp_bytes(int m, int n, int dc, int batch, size_t* msg_bytes, size_
 cudaError_t global_bp_run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8_t* flags, uint32_t* iters,
                           int nframes, int* launches, cudaStream_t st);
 
-// Philox depolarizing errors, bit-packed: errX, errZ [nframes][nw].
-cudaError_t launch_generate(uint64_t seed, uint64_t first_frame, int nframes, int n, int nw, Thresholds thr,
-                            uint32_t* errX, uint32_t* errZ, cudaStream_t st);
+// Philox depolarizing errors, bit-packed: errX, errZ [nframes][nw], and their syndromes synX [nframes][mwX],
+// synZ [nframes][mwZ] in the same kernel (synX == nullptr: errors only).
+cudaError_t launch_generate_syndrome(uint64_t seed, uint64_t first_frame, int nframes, int n, int nw, Thresholds thr,
+                                     uint32_t* errX, uint32_t* errZ, const uint16_t* vchkX, int dvX, int mwX,
+                                     uint32_t* synX, const uint16_t* vchkZ, int dvZ, int mwZ, uint32_t* synZ,
+                                     cudaStream_t st);
 // s = H e (mod 2) for both sides from bit-packed errors; vchk = CSC tables [dv][n] (check index of the k-th edge).
 cudaError_t launch_syndrome(const uint32_t* errX, const uint32_t* errZ, int nframes, int n, int nw,
                             const uint16_t* vchkX, int dvX, int mwX, uint32_t* synX, const uint16_t* vchkZ, int dvZ,
@@ -48,6 +51,14 @@ cudaError_t launch_syndrome(const uint32_t* errX, const uint32_t* errZ, int nfra
 // rows of `bits` one-per-element (elem_size 1 or 4 bytes) <-> bit-packed words
 cudaError_t launch_pack(const void* src, int elem_size, int64_t rows, int cols, int words, uint32_t* dst, cudaStream_t st);
 cudaError_t launch_unpack(const uint32_t* src, int64_t rows, int cols, int words, uint8_t* dst, cudaStream_t st);
+
+// low-latency Decode path: both syndrome rows (one byte per bit) packed by one launch; corrections as bytes, ErrorCode
+// bits and iteration counts [rows][2] produced by one launch
+cudaError_t launch_pack2(const uint8_t* srcX, int colsX, int wordsX, uint32_t* dstX, const uint8_t* srcZ, int colsZ,
+                         int wordsZ, uint32_t* dstZ, int rows, cudaStream_t st);
+cudaError_t launch_finish_small(const uint32_t* decX, const uint32_t* decZ, int rows, int cols, int words, uint8_t* outX,
+                                uint8_t* outZ, const uint8_t* sfX, const uint8_t* sfZ, uint8_t* flags, const uint32_t* itX,
+                                const uint32_t* itZ, uint32_t* iters, cudaStream_t st);
 
 struct StatsArgs {
   const uint32_t *errX, *errZ, *decX, *decZ;  // [nframes][nw]

@@ -37,7 +37,7 @@ def test_cpp_class_surface(host_check, oracle, tmp_path):
     out = subprocess.run([host_check, str(tmp_path / "code.txt")], check=True, capture_output=True, text=True).stdout
     lines = out.splitlines()
     assert "name [J=4,K=5,L=10,P=61,s=9,t=49][[n=610,k=61]]" in lines
-    assert "dims 610 244 305 244x610 678x1220" in lines
+    assert "dims 610 244 305 244x610 1220x1220" in lines
     assert "hHC0 1 9 20 58 34 42 12 47 57 25" in lines
     assert "syndrome_weight 4" in lines
     assert "row_is_logical 0 single_is_logical 1" in lines
@@ -98,3 +98,58 @@ def test_cli_depolarizing_matches_library(cli, qldpc, tmp_path):
     k = qldpc.Decoder(code, 0, 20000).get_statistics_depolarizing(77, 0, 20000, 0.05, 50)["counters"]
     assert "Corrected: %d\n" % int(k[3]) in text and "Logical Errors: %d\n" % int(k[6]) in text
     assert "Errors Tested: 20000\n" in text and "Rand Seed: 77\n" in text
+
+
+@pytest.mark.gpu
+def test_cli_sweep_stop_rule_and_intervals(cli, qldpc, tmp_path):
+    """--sweep p0:p1:k --target-errors E: every point keeps adding batches of COUNT frames of ONE continued global frame
+    stream until it has seen E frame errors (or --max-frames); the record per point is in the reference's results-file
+    format, the summary line carries the Wilson interval, and the counters do not depend on the device count."""
+    import torch
+    count, target, cap, seed, maxit = 2000, 60, 12000, 321, 50
+    name = "[J=4,K=5,L=10,P=61,s=9,t=49][[n=610,k=61]]"
+    code = qldpc.Code.qc(4, 5, 10, 61, 9, 49)
+    dec = qldpc.Decoder(code, 0, count)
+    summaries = []
+    for gpus in ([1, 2] if torch.cuda.device_count() >= 2 else [1]):
+        d = tmp_path / ("g%d" % gpus)
+        d.mkdir()
+        (d / "init.txt").write_text("qc:4,5,10,61,9,49\n0\n0\n%d\n%d\n0.5" % (count, maxit))
+        subprocess.run([cli, "init.txt", "--sweep", "0.03:0.07:3", "--target-errors", str(target), "--max-frames", str(cap),
+                        "--seed", str(seed), "--gpus", str(gpus)], cwd=d, check=True)
+        rows = [ln.split() for ln in (d / "results" / (name + "_sweep_MAX_%d.txt" % maxit)).read_text().splitlines()
+                if not ln.startswith("#")]
+        assert len(rows) == 3
+        summaries.append(rows)
+        for i, row in enumerate(rows):
+            p = np.float32(0.03 + 0.04 * i / 2)
+            frames, bad = int(row[1]), int(row[2])
+            # stop rule: whole batches; stops at the first batch boundary with >= target errors, or at the cap
+            assert frames % count == 0 and frames <= cap
+            k = np.zeros(qldpc.NUM_COUNTERS, np.uint64)
+            done = 0
+            while True:
+                k += dec.get_statistics_depolarizing(seed, (i << 40) + done, count, float(p), maxit)["counters"]
+                done += count
+                if done >= cap or int(k[0]) - int(k[3]) >= target:
+                    break
+            assert frames == done and bad == int(k[0]) - int(k[3])
+            assert int(row[6]) == int(k[6]) and int(row[7]) == int(k[4]) and int(row[8]) == int(k[5])
+            # Wilson 95% interval
+            z, ph = 1.959963984540054, bad / frames
+            den = 1 + z * z / frames
+            ctr, half = (ph + z * z / (2 * frames)) / den, z * np.sqrt(ph * (1 - ph) / frames + z * z / (4.0 * frames * frames)) / den
+            assert abs(float(row[4]) - (ctr - half)) < 1e-5 and abs(float(row[5]) - (ctr + half)) < 1e-5
+            assert float(row[4]) <= ph <= float(row[5])
+            # the per-point record in the reference's format
+            text = (d / "results" / (name + "_depolarizing_MAX_%d_p_%s.txt" % (maxit, row[0]))).read_text()
+            assert "Errors Tested: %d\n" % frames in text and "Corrected: %d\n" % int(k[3]) in text
+            assert "Rand Seed: %d\n" % seed in text and text.startswith("Code: " + name + "\n")
+    if len(summaries) == 2:
+        assert summaries[0] == summaries[1]
+
+
+def test_cli_rejects_wide_seed(cli, tmp_path):
+    (tmp_path / "init.txt").write_text("qc:3,3,6,7,2,3\n1\n1\n10\n20\n0.02")
+    r = subprocess.run([cli, "init.txt", "--depolarizing", "--seed", str(1 << 33)], cwd=tmp_path, capture_output=True, text=True)
+    assert r.returncode == 1 and "32 bits" in r.stderr

@@ -444,3 +444,36 @@ def test_decoders_of_different_codes_coexist(qldpc, oracle):
         assert np.array_equal(a, ob.run_depolarizing(3, 100 * rnd, 48, 0.03, 30)["counters"])
         b = ds.get_statistics_depolarizing(3, 100 * rnd, 2000, 0.03, 30)["counters"]
         assert np.array_equal(b, osm.run_depolarizing(3, 100 * rnd, 2000, 0.03, 30)["counters"])
+
+
+def test_small_batch_path_matches_pipelined_path(qldpc, decoders):
+    """qldpc_decode_batch takes a low-latency path (one stream, no host threads, X and Z side by side) for batches of
+    up to 2048 frames; the same frames inside a larger, pipelined call must come back identical -- also one by one,
+    the way a reference-style per-frame loop calls Decode (DecoderCPU.h:477)."""
+    gc, dec = decoders("C2", 1 << 13)
+    nf = 5000
+    _, _, sx, sz = dec.debug_generate(321, 11, nf, 0.05)
+    big = dec.decode_batch(sx, sz, 0.05, 50)
+    for lo, hi in ((0, 2048), (2048, 2049), (2049, 2100), (4999, 5000)):
+        part = dec.decode_batch(sx[lo:hi], sz[lo:hi], 0.05, 50)
+        for a, b in zip(part, big):
+            assert np.array_equal(a, b[lo:hi])
+
+
+def test_generic_and_specialised_kernels_agree(qldpc, oracle):
+    """J4K5L10P61 runs kernels with the check count as a compile-time constant; QLDPC_NO_SPECIALIZE=1 forces the generic
+    instantiation (any code with the same degrees).  Both must reproduce the oracle frame by frame."""
+    import os
+    gc = qldpc.Code.qc(*CODES["C2"])
+    oc = oracle_code(oracle, "C2", gc.dense_matrix(2))
+    want = oc.run_depolarizing(77, 3, 3000, 0.05, 50)
+    try:
+        for flag in ("1", "0"):
+            os.environ["QLDPC_NO_SPECIALIZE"] = flag
+            dec = qldpc.Decoder(gc, 0, 4096)
+            got = dec.get_statistics_depolarizing(77, 3, 3000, 0.05, 50, per_frame=True)
+            assert np.array_equal(got["counters"], want["counters"])
+            assert np.array_equal(got["flags"], want["flags"])
+            assert np.array_equal(got["iters"], want["iters"].astype(np.uint32))
+    finally:
+        os.environ.pop("QLDPC_NO_SPECIALIZE", None)

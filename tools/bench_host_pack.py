@@ -26,7 +26,7 @@ def main():
             hz = torch.empty_like(hx, pin_memory=pinned)
             hx.numpy()[:] = x
             hz.numpy()[:] = z
-            for threads in (0, 4, 8, 16, 24, 32):
+            for threads in (0, 2, 4, 6, 8, 10, 12, 14, 16):
                 dec.set_host_threads(threads)
                 fn = dec.get_stats_from_errors_ptr
                 k = fn(hx.data_ptr(), hz.data_ptr(), frames, 0.05, 50, dtype().itemsize)
