@@ -11,11 +11,15 @@
 // convergence cadence and `last` iteration; a slot that stops is syndrome-checked, written out and handed the next
 // frame of a queue in the same pass, so slots never idle while frames remain (no lock-step batches).
 //
-// One pass = g_check, g_var (+ its last-iteration variant), g_control, then the kernels that serve the slots which
-// just stopped: g_verify, g_pack, g_handover, g_fill.  Everything a stopped slot needs is produced in slot-innermost
-// arrays by the passes themselves (the variable kernel writes the hard decision of every slot that is at a
-// convergence checkpoint, one byte per variable), so these kernels stay coalesced even though the stopped slots are
-// scattered; a fresh slot is not initialised at all -- its first check phase substitutes the prior for the messages.
+// One pass = g_check, g_var (+ its last-iteration variant), g_control, then the three kernels that serve the slots
+// which just stopped: g_verify_pack (syndrome of the decision; decision words of the frame out), g_handover (flags and
+// iteration count out, next frame in) and g_fill (its syndrome bits).  Everything a stopped slot needs is produced by the passes themselves in BIT-PACKED,
+// slot-innermost arrays -- one 32-bit word holds the bit of 32 consecutive slots: synw[check][S/32] (input syndrome),
+// decw[variable][S/32] (hard decision, written by the variable kernel for every slot at a convergence checkpoint) --
+// so serving the scattered stopped slots costs (m + E + n) * S / 8 bytes per pass, about 1% of the message traffic.
+// A fresh slot is not initialised at all: its first check phase substitutes the prior for the messages.
+// The host never synchronises inside a run: the completion count is mirrored into mapped pinned memory by g_control
+// and read there; passes are enqueued at most 8 ahead of the device.
 #include <algorithm>
 #include <cstdint>
 
@@ -33,16 +37,18 @@ constexpr int kGroup = 256;  // slots per control block
 
 struct Slots {
   float* msg;          // [E][S]
-  uint8_t* synb;       // [m][S] input syndrome bit of the frame in the slot
+  uint32_t* synw;      // [m][S/32] input syndrome bits of the frames in the slots (bit = slot % 32)
+  uint32_t* decw;      // [n][S/32] hard decision after the last checkpoint variable phase
+  uint32_t* mismatchw; // [S/32] decision syndrome != input syndrome, for the slots that just stopped
+  uint32_t* donew;     // [S/32] slots in state kDone
   uint8_t* state;      // [S]
   uint8_t* bad;        // [S] an unconverged message was seen in the last variable phase
   uint8_t* nanflag;    // [S] a NaN message was seen in the last checkpoint variable phase
-  uint8_t* mismatch;   // [S]
-  uint8_t* decb;       // [n][S] hard decision after the last checkpoint variable phase, one byte per bit
   int32_t* frame;      // [S] frame id in the slot
   int32_t* iter;       // [S] iteration index n of the slot
   unsigned int* ctr;   // [0] next frame to hand out, [1] frames completed, [2], [3] lengths of the two `lastq` lists
   uint32_t* lastq;     // [2][S] thread indices (slot / W) of the variable kernel with a slot entering its last iteration
+  unsigned int* host_done;  // mapped pinned memory: mirror of ctr[1] for the host
 };
 
 // Every slot starts "stopped" with no frame to write out: g_handover gives it its first frame.
@@ -52,9 +58,14 @@ __global__ void __launch_bounds__(kGroup) g_start(Slots s, int S) {
     s.state[t] = kDone;
     s.frame[t] = -1;
     s.iter[t] = 0;
-    s.bad[t] = s.nanflag[t] = s.mismatch[t] = 0;
+    s.bad[t] = s.nanflag[t] = 0;
+  }
+  if (t < S / 32) {
+    s.donew[t] = 0xFFFFFFFFu;
+    s.mismatchw[t] = 0u;
   }
   if (t < 4) s.ctr[t] = 0;
+  if (t == 0) *s.host_done = 0u;
 }
 
 // W consecutive slots per thread, moved with one 4*W-byte access per message row: a pass is bound by HBM, and wide
@@ -121,12 +132,11 @@ __global__ void __launch_bounds__(128) g_check(Slots s, int m, int dc_rt, int S,
           if (st[w] == kFresh) t[i][w] = tp;
       }
   }
-  uint8_t sb[W];
-  ld_b<W>(sb, s.synb + (size_t)e * S + f);
+  const uint32_t sw = s.synw[(size_t)e * (S >> 5) + (f >> 5)] >> (f & 31);  // W divides 32: one word holds the W bits
   float cf[W], pre[W];
 #pragma unroll
   for (int w = 0; w < W; ++w) {
-    cf[w] = sb[w] ? 0.5f : -0.5f;  // DecoderCPU.h:178-183, see bp_kernel.cuh
+    cf[w] = (sw >> w) & 1u ? 0.5f : -0.5f;  // DecoderCPU.h:178-183, see bp_kernel.cuh
     pre[w] = 1.0f;
   }
 #pragma unroll
@@ -156,33 +166,42 @@ __global__ void __launch_bounds__(128) g_check(Slots s, int m, int dc_rt, int S,
 // The latter works from the list g_control compiled in the previous pass (`lastq`, usually empty or short), or
 // over all threads if `lastq` is null (one-iteration runs, where every slot is in its last iteration).
 template <int MAXV, int W, bool EXACT, bool LAST>
-__global__ void __launch_bounds__(128) g_var(Slots s, const uint32_t* __restrict__ vrow, int n, int dv_rt, int S,
-                                             float prior, int last_it, const uint32_t* __restrict__ lastq,
-                                             const unsigned int* __restrict__ lastq_len) {
+__device__ __forceinline__ void g_var_body(const Slots& s, const uint32_t* __restrict__ vrow, int n, int dv_rt, int S,
+                                           float prior, int last_it, int t, int v) {
   const int dv = EXACT ? MAXV : dv_rt;
-  int t = blockIdx.x * blockDim.x + threadIdx.x;
-  if (LAST && lastq) {
-    if (t >= (int)*lastq_len) return;
-    t = (int)lastq[t];
-  }
   const int f = t * W;
-  const int v = blockIdx.y;
-  if (f >= S) return;
+  const int SW = S >> 5;
   uint8_t st[W];
-  ld_b<W>(st, s.state + f);
   int it[W];
-  ld_i<W>(it, s.iter + f);
   bool any = false, anylast = false, anyck = false, last[W], ck[W];
 #pragma unroll
-  for (int w = 0; w < W; ++w) {
-    const bool run = running(st[w]);
-    last[w] = run && it[w] == last_it;              // DecoderCPU.h:284
-    ck[w] = run && (last[w] || it[w] % 10 == 0);    // DecoderCPU.h:287
-    any |= run;
-    anylast |= last[w];
-    anyck |= ck[w];
+  for (int w = 0; w < W; ++w) { st[w] = kIdle; it[w] = 0; last[w] = ck[w] = false; }
+  if (f < S) {
+    ld_b<W>(st, s.state + f);
+    ld_i<W>(it, s.iter + f);
+#pragma unroll
+    for (int w = 0; w < W; ++w) {
+      const bool run = running(st[w]);
+      last[w] = run && it[w] == last_it;              // DecoderCPU.h:284
+      ck[w] = run && (last[w] || it[w] % 10 == 0);    // DecoderCPU.h:287
+      any |= run;
+      anylast |= last[w];
+      anyck |= ck[w];
+    }
   }
-  if (!any || anylast != LAST) return;
+  const bool active = any && anylast == LAST;
+  // The LAST = false launch keeps whole warps alive: the decision bits of 32 consecutive slots share a word, which
+  // the lanes assemble together below.  The list-driven LAST = true launch has no such alignment and uses atomics.
+  if (!active) {
+    if (LAST) return;
+    anyck = false;
+#pragma unroll
+    for (int w = 0; w < W; ++w) ck[w] = false;
+  }
+  uint8_t bit[W];
+#pragma unroll
+  for (int w = 0; w < W; ++w) bit[w] = 0;
+  if (active) {
   // Only the messages are kept in registers; the complements 1 - p are recomputed where they are used (one FADD,
   // same rounding), which is cheaper than the occupancy their registers would cost a bandwidth-bound kernel.
   float pk[MAXV][W];
@@ -213,9 +232,65 @@ __global__ void __launch_bounds__(128) g_var(Slots s, const uint32_t* __restrict
       }
   }
   bool anybad[W], anynan[W];
-  uint8_t bit[W];
 #pragma unroll
-  for (int w = 0; w < W; ++w) { anybad[w] = anynan[w] = false; bit[w] = 0; }
+  for (int w = 0; w < W; ++w) anybad[w] = anynan[w] = false;
+  if constexpr (!LAST && W % 2 == 0) {
+    // Hot variant: two slots per instruction with the packed fp32x2 arithmetic of sm_100 (bp_kernel.cuh: Pack<2>), each
+    // half an independent IEEE operation.  The variable kernel issues ~60% of its slots with scalar arithmetic, which
+    // keeps it below the HBM roofline; packing halves the multiplies and the division's FMAs.
+    constexpr int H = W / 2;
+    typedef Pack<2> P2;
+    P2 pk2[MAXV][H], om2[MAXV][H], pP[H], pQ[H];
+#pragma unroll
+    for (int k = 0; k < MAXV; ++k)
+      if (k < dv) {
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          pk2[k][h] = P2::load(&pk[k][2 * h]);
+          om2[k][h] = pfma(pk2[k][h], P2::splat(-1.0f), P2::splat(1.0f));  // 1 - p, one rounding (DecoderCPU.h:220)
+        }
+      }
+#pragma unroll
+    for (int h = 0; h < H; ++h) { pP[h] = P2::splat(prior); pQ[h] = P2::splat(prior1); }
+#pragma unroll
+    for (int j = 0; j < MAXV; ++j) {
+      if (j < dv) {
+        float q[W];
+#pragma unroll
+        for (int h = 0; h < H; ++h) {
+          P2 P = pP[h], Q = pQ[h];
+#pragma unroll
+          for (int k = j + 1; k < MAXV; ++k)
+            if (k < dv) {
+              Q = pmul(Q, om2[k][h]);
+              P = pmul(P, pk2[k][h]);
+            }
+          P2 nden;  // -(Q + P) by scalar adds: ptxas would contract a packed mul + add into one FFMA2 (bp_kernel.cuh)
+          nden.set(0, __fadd_rn(-Q.get(0), -P.get(0)));
+          nden.set(1, __fadd_rn(-Q.get(1), -P.get(1)));
+          bool unsafe = false;
+          P2 out = div_fast_pack<3, 2>(P, nden, unsafe);  // == P / (Q + P), DecoderCPU.h:223
+          if (unsafe) {
+            out.set(0, __fdiv_rn(P.get(0), -nden.get(0)));
+            out.set(1, __fdiv_rn(P.get(1), -nden.get(1)));
+          }
+          q[2 * h] = out.get(0);
+          q[2 * h + 1] = out.get(1);
+          if (j < dv - 1) {
+            pQ[h] = pmul(pQ[h], om2[j][h]);
+            pP[h] = pmul(pP[h], pk2[j][h]);
+          }
+        }
+#pragma unroll
+        for (int w = 0; w < W; ++w) {
+          anybad[w] |= unconverged(q[w]);
+          anynan[w] |= q[w] != q[w];
+          bit[w] |= q[w] >= 0.5f;  // hard decision: any edge message >= 0.5f (DecoderCPU.h:354-373)
+        }
+        st_f<W>(s.msg + (size_t)row[j] * S + f, q);
+      }
+    }
+  } else {
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
     if (j < dv) {
@@ -248,28 +323,78 @@ __global__ void __launch_bounds__(128) g_var(Slots s, const uint32_t* __restrict
       st_f<W>(s.msg + (size_t)row[j] * S + f, q);
     }
   }
-  if (!anyck) return;
-  // A slot can only stop at a checkpoint, so this is where its decision is recorded (lanes that are not at one get
-  // a value nobody reads).
-  st_b<W>(s.decb + (size_t)v * S + f, bit);
+  }
 #pragma unroll
   for (int w = 0; w < W; ++w)
     if (ck[w]) {
       if (anybad[w]) s.bad[f + w] = 1;
       if (anynan[w]) s.nanflag[f + w] = 1;
     }
+  }  // active
+  // A slot can only stop at a checkpoint, so this is where its decision is recorded: bit (slot % 32) of
+  // decw[v][slot / 32], only for the slots that are at a checkpoint in this pass.
+  uint32_t val = 0, mask = 0;
+#pragma unroll
+  for (int w = 0; w < W; ++w) {
+    val |= (uint32_t)(bit[w] & 1u) << w;
+    mask |= (uint32_t)ck[w] << w;
+  }
+  if (LAST) {
+    if (mask) {
+      uint32_t* word = s.decw + (size_t)v * SW + (f >> 5);
+      const int sh = f & 31;
+      atomicAnd(word, ~((mask & ~val) << sh));
+      atomicOr(word, (mask & val) << sh);
+    }
+    return;
+  }
+  if (!__any_sync(0xffffffffu, anyck)) return;
+  constexpr int G = 32 / W;  // lanes per word
+  const int lane = threadIdx.x & 31, sh = W * (lane % G);
+  val <<= sh;
+  mask <<= sh;
+#pragma unroll
+  for (int d = 1; d < G; d <<= 1) {
+    val |= __shfl_xor_sync(0xffffffffu, val, d);
+    mask |= __shfl_xor_sync(0xffffffffu, mask, d);
+  }
+  if (lane % G == 0 && mask && f < S) {
+    uint32_t* word = s.decw + (size_t)v * SW + (f >> 5);
+    *word = (*word & ~mask) | (val & mask);
+  }
 }
 
-// BeliefPropogation loop control (DecoderCPU.h:280-291), per slot, after the variable phase.
+template <int MAXV, int W, bool EXACT, bool LAST>
+__global__ void __launch_bounds__(128) g_var(Slots s, const uint32_t* __restrict__ vrow, int n, int dv_rt, int S,
+                                             float prior, int last_it, const uint32_t* __restrict__ lastq,
+                                             const unsigned int* __restrict__ lastq_len) {
+  const int t = blockIdx.x * blockDim.x + threadIdx.x;
+  if (LAST && lastq) {
+    // The list-driven launch uses a small grid and strides over the list: it is short or empty in almost every pass,
+    // and a full-size grid of threads that only find that out costs as much as a tenth of a pass.
+    const int len = (int)*lastq_len;
+    for (int li = t; li < len; li += gridDim.x * blockDim.x)
+      g_var_body<MAXV, W, EXACT, LAST>(s, vrow, n, dv_rt, S, prior, last_it, (int)lastq[li], blockIdx.y);
+  } else {
+    g_var_body<MAXV, W, EXACT, LAST>(s, vrow, n, dv_rt, S, prior, last_it, t, blockIdx.y);
+  }
+}
+
+// BeliefPropogation loop control (DecoderCPU.h:280-291), per slot, after the variable phase.  Also publishes which
+// slots stopped (one bit per slot, for g_verify / g_finish) and mirrors the completion count for the host.
 __global__ void __launch_bounds__(kGroup) g_control(Slots s, int S, int last_it, int wv, int parity) {
   const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f == 0) s.ctr[2 + (parity ^ 1)] = 0;  // the list the next pass's g_control appends to; its reader has run
-  bool next_is_last = false;
+  if (f == 0) {
+    s.ctr[2 + (parity ^ 1)] = 0;  // the list the next pass's g_control appends to; its reader has run
+    *s.host_done = s.ctr[1];      // every frame counted here has all its outputs written (earlier kernels)
+  }
+  bool next_is_last = false, done = false;
   if (f < S && running(s.state[f])) {
     const int it = s.iter[f];
     const bool last = it == last_it, ck = last || it % 10 == 0;
     if (last || (ck && !s.bad[f])) {
       s.state[f] = kDone;  // bad / nanflag are kept: CONVERGENCE_FAIL and the NaN bit describe the final state
+      done = true;
     } else {
       s.state[f] = kRun;
       s.iter[f] = it + 1;
@@ -277,94 +402,124 @@ __global__ void __launch_bounds__(kGroup) g_control(Slots s, int S, int last_it,
       next_is_last = it + 1 == last_it;
     }
   }
+  const int lane = threadIdx.x & 31;
+  const unsigned donemask = __ballot_sync(0xffffffffu, done);
+  if (lane == 0 && f < S) s.donew[f >> 5] = donemask;
   // one list entry per variable-kernel thread (wv consecutive slots): the lowest flagged slot of the group appends
   const unsigned flagged = __ballot_sync(0xffffffffu, next_is_last);
-  const int lane = threadIdx.x & 31, first = lane & ~(wv - 1);
+  const int first = lane & ~(wv - 1);
   const unsigned group = (flagged >> first) & ((1u << wv) - 1u);
   if (next_is_last && (group & ((1u << (lane - first)) - 1u)) == 0)
     s.lastq[(size_t)parity * S + atomicAdd(&s.ctr[2 + parity], 1u)] = (uint32_t)(f / wv);
 }
 
-// syndrome of the decision against the input syndrome (DecoderCPU.h:380-384), for the slots that just stopped
-__global__ void __launch_bounds__(128) g_verify(Slots s, const uint32_t* __restrict__ cvar, int m, int dc, int S) {
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (f >= S) return;
-  uint8_t st[4];
-  ld_b<4>(st, s.state + f);
-  if (st[0] != kDone && st[1] != kDone && st[2] != kDone && st[3] != kDone) return;
-  unsigned any = 0;
-  for (int e = blockIdx.y; e < m; e += gridDim.y) {
-    unsigned par = *reinterpret_cast<const uint32_t*>(s.synb + (size_t)e * S + f);  // 4 slots, one byte each
-    for (int i = 0; i < dc; ++i)
-      par ^= *reinterpret_cast<const uint32_t*>(s.decb + (size_t)cvar[(size_t)i * m + e] * S + f);
-    any |= par;
-  }
+// Serves the slots that just stopped, 32 slots (one bit-word) per thread, blockIdx.y striding over work units:
+//  * units [0, m): syndrome of the decision against the input syndrome (DecoderCPU.h:380-384) -- the thread XORs the
+//    decision words of the dc variables of check `unit` onto its syndrome word; any bit left set is a mismatch
+//    (partial results meet in mismatchw by atomicOr);
+//  * units [m, m + nw): word `unit - m` of the packed decision rows of the frames leaving -- a 32 x 32 bit transpose
+//    of decw[32 variables][this word], one output word per stopped slot.
+__global__ void __launch_bounds__(128) g_verify_pack(Slots s, const uint32_t* __restrict__ cvar, int m, int dc, int n,
+                                                     int nw, int S, uint32_t* __restrict__ dec) {
+  const int SW = S >> 5, wi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wi >= SW) return;
+  const uint32_t done = s.donew[wi];
+  if (!done) return;
+  uint32_t any = 0;
+  for (int u = blockIdx.y; u < m + nw; u += gridDim.y) {
+    if (u < m) {
+      uint32_t par = s.synw[(size_t)u * SW + wi];
+      for (int i = 0; i < dc; ++i) par ^= s.decw[(size_t)cvar[(size_t)i * m + u] * SW + wi];
+      any |= par;
+    } else {
+      const int word = u - m, v0 = word * 32, cnt = min(32, n - v0);
+      uint32_t col[32];
 #pragma unroll
-  for (int w = 0; w < 4; ++w)
-    if (st[w] == kDone && ((any >> (8 * w)) & 1u)) s.mismatch[f + w] = 1;
-}
-
-// decision bytes -> bit-packed words of the frame, for the slots that just stopped
-__global__ void __launch_bounds__(128) g_pack(Slots s, int n, int S, int nw, uint32_t* __restrict__ dec) {
-  const int f = (blockIdx.x * blockDim.x + threadIdx.x) * 4;
-  if (f >= S) return;
-  uint8_t st[4];
-  ld_b<4>(st, s.state + f);
-  int fr[4];
-  ld_i<4>(fr, s.frame + f);
-  bool any = false;
+      for (int b = 0; b < 32; ++b) col[b] = b < cnt ? s.decw[(size_t)(v0 + b) * SW + wi] : 0u;
+      uint32_t left = done;
+      while (left) {  // one output word per stopped slot of this thread's 32
+        const int sl = __ffs((int)left) - 1;
+        left &= left - 1u;
+        const int fr = s.frame[wi * 32 + sl];
+        if (fr < 0) continue;
+        uint32_t out = 0;
 #pragma unroll
-  for (int w = 0; w < 4; ++w) {
-    if (st[w] != kDone) fr[w] = -1;
-    any |= fr[w] >= 0;
-  }
-  if (!any) return;
-  for (int word = blockIdx.y; word < nw; word += gridDim.y) {
-    uint32_t out[4] = {0, 0, 0, 0};
-    for (int b = 0; b < 32; ++b) {
-      const int v = word * 32 + b;
-      if (v >= n) break;
-      const uint32_t d = *reinterpret_cast<const uint32_t*>(s.decb + (size_t)v * S + f);
-#pragma unroll
-      for (int w = 0; w < 4; ++w) out[w] |= ((d >> (8 * w)) & 1u) << b;
+        for (int b = 0; b < 32; ++b) out |= ((col[b] >> sl) & 1u) << b;
+        dec[(size_t)fr * nw + word] = out;
+      }
     }
-#pragma unroll
-    for (int w = 0; w < 4; ++w)
-      if (fr[w] >= 0) dec[(size_t)fr[w] * nw + word] = out[w];
   }
+  any &= done;
+  if (any) atomicOr(&s.mismatchw[wi], any);
 }
 
-// per-frame outputs of the stopped slots, then the hand-over to the next frame of the queue
+// Per-frame outputs of the stopped slots, then the hand-over to the next frame of the queue; one warp per 32 slots
+// (lane = slot), one queue atomic per warp.  Leaves the mask of the slots that received a frame in donew (g_fill's input).
 __global__ void __launch_bounds__(kGroup) g_handover(Slots s, int S, int nframes, uint8_t* __restrict__ flags,
                                                      uint32_t* __restrict__ iters) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= S || s.state[f] != kDone) return;
-  const int fr = s.frame[f];
+  const int f = blockIdx.x * blockDim.x + threadIdx.x, lane = threadIdx.x & 31;
+  if (f - lane >= S) return;  // S is a multiple of 32: whole warps
+  const int wi = f >> 5;
+  const uint32_t donemask = s.donew[wi];
+  if (!donemask) return;
+  const bool done = (donemask >> lane) & 1u;
+  const int fr = done ? s.frame[f] : -1;
   if (fr >= 0) {
     // CONVERGENCE_FAIL = !CheckConvergence(final messages), DecoderCPU.h:375-378
-    flags[fr] = (uint8_t)((s.mismatch[f] & 1u) | ((s.bad[f] & 1u) << 1) | ((s.nanflag[f] & 1u) << 2));
+    const uint32_t mis = (s.mismatchw[wi] >> lane) & 1u;
+    flags[fr] = (uint8_t)(mis | ((s.bad[f] & 1u) << 1) | ((s.nanflag[f] & 1u) << 2));
     iters[fr] = (uint32_t)(s.iter[f] + 1);
-    atomicAdd(&s.ctr[1], 1u);
   }
-  const unsigned next = atomicAdd(&s.ctr[0], 1u);
-  s.bad[f] = s.nanflag[f] = s.mismatch[f] = 0;
-  s.iter[f] = 0;
-  if (next < (unsigned)nframes) {
-    s.frame[f] = (int)next;
-    s.state[f] = kFresh;
-  } else {
-    s.frame[f] = -1;
-    s.state[f] = kIdle;
+  const unsigned leaving = __ballot_sync(0xffffffffu, fr >= 0);
+  unsigned base = 0;
+  if (lane == 0) {
+    if (leaving) atomicAdd(&s.ctr[1], (unsigned)__popc(leaving));
+    base = atomicAdd(&s.ctr[0], (unsigned)__popc(donemask));
+  }
+  base = __shfl_sync(0xffffffffu, base, 0);
+  int next = -1;
+  if (done) {
+    const unsigned ticket = base + (unsigned)__popc(donemask & ((1u << lane) - 1u));
+    next = ticket < (unsigned)nframes ? (int)ticket : -1;
+    s.bad[f] = s.nanflag[f] = 0;
+    s.iter[f] = 0;
+    s.frame[f] = next;
+    s.state[f] = next >= 0 ? kFresh : kIdle;
+  }
+  const unsigned fresh = __ballot_sync(0xffffffffu, next >= 0);
+  if (lane == 0) {
+    s.mismatchw[wi] = 0u;
+    s.donew[wi] = fresh;  // consumed (and cleared for the next pass by g_control's rewrite) by g_fill
   }
 }
 
-// syndrome bits of the frames just handed out -> one byte per (check, slot).  Runs right after g_handover, when
-// kFresh marks exactly the new arrivals (g_control turns kFresh into kRun after their first iteration).
+// Syndrome bits of the frames just handed out: bit `slot % 32` of synw[e][slot / 32]; the other slots of the word keep
+// theirs.  One thread per word, blockIdx.y striding over the checks.
 __global__ void __launch_bounds__(128) g_fill(Slots s, const uint32_t* __restrict__ syn, int mw, int m, int S) {
-  const int f = blockIdx.x * blockDim.x + threadIdx.x;
-  if (f >= S || s.state[f] != kFresh) return;
-  const uint32_t* row = syn + (size_t)s.frame[f] * mw;
-  for (int e = blockIdx.y; e < m; e += gridDim.y) s.synb[(size_t)e * S + f] = (uint8_t)((row[e >> 5] >> (e & 31)) & 1u);
+  const int SW = S >> 5, wi = blockIdx.x * blockDim.x + threadIdx.x;
+  if (wi >= SW) return;
+  const uint32_t fresh = s.donew[wi];
+  if (!fresh) return;
+  for (int ew = blockIdx.y; ew < mw; ew += gridDim.y) {  // 32 checks per step: one syndrome word of every fresh frame
+    uint32_t col[32];
+    uint32_t left = fresh;
+#pragma unroll
+    for (int b = 0; b < 32; ++b) col[b] = 0u;
+    while (left) {
+      const int sl = __ffs((int)left) - 1;
+      left &= left - 1u;
+      const uint32_t w = syn[(size_t)s.frame[wi * 32 + sl] * mw + ew];
+#pragma unroll
+      for (int b = 0; b < 32; ++b) col[b] |= ((w >> b) & 1u) << sl;
+    }
+    const int cnt = min(32, m - ew * 32);
+#pragma unroll
+    for (int b = 0; b < 32; ++b)
+      if (b < cnt) {
+        uint32_t* word = s.synw + (size_t)(ew * 32 + b) * SW + wi;
+        *word = (*word & ~fresh) | col[b];
+      }
+  }
 }
 
 using CheckFn = void (*)(Slots, int, int, int, float);
@@ -402,53 +557,75 @@ cudaError_t run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8
   const long long asked = a.slots > 0 ? ((long long)a.slots + 31) / 32 * 32 : (want + 127) / 128 * 128;
   const int S = (int)std::max<long long>(32, std::min<long long>(a.batch, asked));
   Slots s;
+  const int SW = S / 32;
   s.msg = a.msg;
-  s.synb = a.bytes;
-  s.state = s.synb + (size_t)m * S;
+  s.state = a.bytes;
   s.bad = s.state + S;
   s.nanflag = s.bad + S;
-  s.mismatch = s.nanflag + S;
-  s.decb = s.mismatch + S;
-  s.frame = (int32_t*)a.words;
+  s.synw = a.words;
+  s.decw = s.synw + (size_t)m * SW;
+  s.mismatchw = s.decw + (size_t)n * SW;
+  s.donew = s.mismatchw + SW;
+  s.frame = (int32_t*)(a.words + ((size_t)(m + n + 2) * SW + 3) / 4 * 4);  // 16-byte aligned for the 4-slot loads
   s.iter = s.frame + S;
   s.ctr = (unsigned int*)(s.iter + S);
   s.lastq = s.ctr + 4;
+  s.host_done = a.host_done;
   CheckFn check = nullptr;
   VarFn var = nullptr, var_last = nullptr;
   int wc = 1, wv = 1;
   pick_check(a.dc, check, wc);
   pick_var(a.dv, var, var_last, wv);
-  const int sb = (S + kGroup - 1) / kGroup, s1 = (S + 127) / 128, s4 = (S + 511) / 512;
+  const int sb = (S + kGroup - 1) / kGroup;
   const dim3 gc((S + 128 * wc - 1) / (128 * wc), m), gv((S + 128 * wv - 1) / (128 * wv), n);
-  const dim3 ge(s4, std::min(m, 32)), gp(s4, std::min(a.nw, 32)), gf(s1, std::min(m, 16));
+  // the bit-word kernels: SW / 128 blocks of words, times enough y-strides over their units to fill the machine
+  const int vx = (SW + 127) / 128;
+  const dim3 ge(vx, std::max(1, std::min(m + a.nw, 4096 / std::max(vx, 1))));
+  const dim3 gf(vx, std::max(1, std::min(a.mw, 4096 / std::max(vx, 1))));
   const int last_it = a.maxit - 1;
   g_start<<<sb, kGroup, 0, st>>>(s, S);
   // A pass first serves the slots that stopped in the previous pass (before the first pass: all of them, with no
-  // frame to write out), then runs one BP iteration on every running slot.
-  for (long long pass = 0;; ++pass) {
-    if (pass > 0) {
-      g_verify<<<ge, 128, 0, st>>>(s, a.cvar, m, a.dc, S);
-      g_pack<<<gp, 128, 0, st>>>(s, n, S, a.nw, dec);
+  // frame to write out), then runs one BP iteration on every running slot.  Completion is read from mapped pinned
+  // memory (g_control mirrors the count there); the host enqueues at most kAhead passes beyond the one it has seen
+  // finish, so the device never waits for the host and the host never synchronises the stream inside a run.
+  // Passes enqueued after the last frame has left find every slot idle and return at once.
+  constexpr int kAhead = 8;
+  cudaEvent_t ev[kAhead];
+  for (int i = 0; i < kAhead; ++i) {
+    cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+    if (e != cudaSuccess) {
+      for (int j = 0; j < i; ++j) cudaEventDestroy(ev[j]);
+      return e;
     }
+  }
+  cudaError_t err = cudaSuccess;
+  volatile unsigned int* host_done = a.host_done;
+  for (long long pass = 0;; ++pass) {
+    if (pass >= kAhead) {
+      err = cudaEventSynchronize(ev[pass % kAhead]);  // pass - kAhead has finished
+      if (err != cudaSuccess) break;
+      if (*host_done >= (unsigned)nframes) break;
+    }
+    if (pass > 0) g_verify_pack<<<ge, 128, 0, st>>>(s, a.cvar, m, a.dc, n, a.nw, S, dec);
     g_handover<<<sb, kGroup, 0, st>>>(s, S, nframes, flags, iters);
     g_fill<<<gf, 128, 0, st>>>(s, syn, a.mw, m, S);
-    if (pass % 8 == 0) {  // completion is polled every few passes (a device-to-host copy and a stream sync)
-      unsigned int completed = 0;
-      cudaError_t e = cudaMemcpyAsync(&completed, s.ctr + 1, sizeof completed, cudaMemcpyDeviceToHost, st);
-      if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-      if (e != cudaSuccess) return e;
-      if (completed >= (unsigned)nframes) break;
-    }
     check<<<gc, 128, 0, st>>>(s, m, a.dc, S, a.prior);
     const int parity = (int)(pass & 1);
     var<<<gv, 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.prior, last_it, nullptr, nullptr);
     if (last_it == 0)
       var_last<<<gv, 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.prior, last_it, nullptr, nullptr);
     else if (pass >= last_it)  // no slot is that old before; the list was written by the previous pass's g_control
-      var_last<<<gv, 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.prior, last_it, s.lastq + (size_t)(parity ^ 1) * S,
-                                   s.ctr + 2 + (parity ^ 1));
+      var_last<<<dim3(std::min<unsigned>(gv.x, 8u), n), 128, 0, st>>>(s, a.vrow, n, a.dv, S, a.prior, last_it,
+                                                                       s.lastq + (size_t)(parity ^ 1) * S,
+                                                                       s.ctr + 2 + (parity ^ 1));
     g_control<<<sb, kGroup, 0, st>>>(s, S, last_it, wv, parity);
+    err = cudaEventRecord(ev[pass % kAhead], st);
+    if (err != cudaSuccess) break;
+    if (pass == 0 && (err = cudaGetLastError()) != cudaSuccess) break;  // a bad launch configuration shows here
   }
+  if (err == cudaSuccess) err = cudaStreamSynchronize(st);  // drains the (empty) passes enqueued ahead
+  for (int i = 0; i < kAhead; ++i) cudaEventDestroy(ev[i]);
+  if (err != cudaSuccess) return err;
   return cudaGetLastError();
 }
 
@@ -456,8 +633,9 @@ cudaError_t run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8
 
 size_t global_bp_bytes(int m, int n, int dc, int batch, size_t* msg_bytes, size_t* byte_bytes, size_t* word_bytes) {
   *msg_bytes = (size_t)m * dc * batch * sizeof(float);
-  *byte_bytes = ((size_t)m + 4 + n) * batch;
-  *word_bytes = ((size_t)4 * batch + 4) * sizeof(uint32_t);
+  *byte_bytes = (size_t)3 * batch;  // state, bad, nanflag
+  // synw, decw [m + n][batch / 32], mismatchw, donew [batch / 32], frame, iter [batch], 4 counters, lastq [2][batch]
+  *word_bytes = ((size_t)(m + n + 2) * (batch / 32) + 4 + (size_t)4 * batch + 4) * sizeof(uint32_t);
   return *msg_bytes + *byte_bytes + *word_bytes;
 }
 

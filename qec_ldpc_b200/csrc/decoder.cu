@@ -58,6 +58,7 @@ struct DevSide {
   float* gmsg = nullptr;
   uint8_t* gbytes = nullptr;
   uint32_t* gwords = nullptr;
+  unsigned int* ghost_done = nullptr;  // mapped pinned completion counter of the HBM-resident path
   int gbatch = 0;
 };
 
@@ -122,6 +123,7 @@ struct qldpc_decoder {
     for (int i = 0; i < 2; ++i) {
       cudaFree(s[i].vrow); cudaFree(s[i].vchk); cudaFree(s[i].gvrow); cudaFree(s[i].gcvar);
       cudaFree(s[i].gmsg); cudaFree(s[i].gbytes); cudaFree(s[i].gwords);
+      if (s[i].ghost_done) cudaFreeHost(s[i].ghost_done);
     }
     cudaFree(errX); cudaFree(errZ); cudaFree(synX); cudaFree(synZ); cudaFree(decX); cudaFree(decZ);
     cudaFree(sfX); cudaFree(sfZ); cudaFree(fflags); cudaFree(itX); cudaFree(itZ);
@@ -291,6 +293,8 @@ int ensure_global(qldpc_decoder* d, int side) {
   const SideTables& t = d->code.side[side];
   const int n = d->n;
   if (std::max(s.dc, s.dv) > 32) return fail(QLDPC_ERR_UNSUPPORTED, "node degree above 32");
+  // the HBM-resident kernels put the node index on gridDim.y (at most 65535)
+  if (n > 65535 || s.m > 65535) return fail(QLDPC_ERR_UNSUPPORTED, "more than 65535 variables or checks per side");
   std::vector<uint32_t> vrow((size_t)t.E), cvar((size_t)t.E);
   for (int v = 0; v < n; ++v)
     for (int k = 0; k < t.dv; ++k) {
@@ -311,6 +315,8 @@ int ensure_global(qldpc_decoder* d, int side) {
   CU_TRY(cudaMemcpy(s.gcvar, cvar.data(), cvar.size() * 4, cudaMemcpyHostToDevice));
   CU_TRY(cudaMalloc((void**)&s.gbytes, bb));
   CU_TRY(cudaMalloc((void**)&s.gwords, wb));
+  CU_TRY(cudaHostAlloc((void**)&s.ghost_done, sizeof(unsigned int), cudaHostAllocMapped));
+  *s.ghost_done = 0u;
   CU_TRY(cudaMalloc((void**)&s.gmsg, mb));
   return QLDPC_OK;
 }
@@ -399,6 +405,7 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
       g.maxit = maxIterations; g.batch = s.gbatch; g.prior = prior;
       g.slots = s.force_global ? s.user.threads : 0;
       g.vrow = s.gvrow; g.cvar = s.gcvar; g.msg = s.gmsg; g.bytes = s.gbytes; g.words = s.gwords;
+      g.host_done = s.ghost_done;
       CU_TRY(global_bp_run(g, a.syn, a.dec, a.flags, a.iters, nf, nullptr, d->stream));
       continue;
     }

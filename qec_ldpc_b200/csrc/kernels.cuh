@@ -31,8 +31,9 @@ struct GlobalBpArgs {
   const uint32_t* vrow;  // [dv][n]
   const uint32_t* cvar;  // [dc][m]
   float* msg;            // [E][batch]
-  uint8_t* bytes;        // syndrome bytes [m][batch], 4 per-slot byte arrays, decision bytes [n][batch]
-  uint32_t* words;       // frame ids [batch], iteration indices [batch], 2 counters
+  uint8_t* bytes;        // 3 per-slot byte arrays
+  uint32_t* words;       // bit-packed syndrome / decision words, frame ids, iteration indices, counters, lists
+  unsigned int* host_done = nullptr;  // mapped pinned word: completion count mirrored for the host (no stream syncs)
 };
 size_t global_bp_bytes(int m, int n, int dc, int batch, size_t* msg_bytes, size_t* byte_bytes, size_t* word_bytes);
 cudaError_t global_bp_run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8_t* flags, uint32_t* iters,
