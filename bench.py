@@ -335,9 +335,11 @@ def run_native(args):
     # ---- end to end through the C ABI with HOST buffers ("e2e") ----------------------------------------------
     # DecoderGPU::GetStats(..., xErrors, zErrors) (DecoderGPU.h:193): pre-generated patterns in host memory, in the
     # reference's layout (one int per qubit, frame-major); host marshalling, H2D copies, decode and the D2H counter
-    # read are all inside the timed region.  The library packs the rows to bits with host threads before the copy (ONE
-    # method for every rank count: min(16, cores / local ranks) threads, at least 1); the raw-rows variant (threads = 0,
-    # the int32 rows cross the link and are packed on the device) is timed beside it every time.
+    # read are all inside the timed region.  The call has two ways to marshal the rows: pack them to bits with host
+    # threads before the copy, or copy the raw rows and pack on the device.  BOTH are timed every time, at every rank
+    # count (host_packed: min(16, cores / local ranks) threads; raw_rows_over_link: threads = 0); `value` is the one the
+    # library picks by default on this box (packing needs >= 6 threads per rank to beat the raw copy of int32 rows),
+    # named in `method`.
     n = code.n
     code_nw = (n + 31) // 32
     xh = torch.empty((F, n), dtype=torch.int32, pin_memory=True)
@@ -351,6 +353,7 @@ def run_native(args):
             zh[off + o:off + o + cnt] = torch.from_numpy(z)
         off += f
     host_threads = q.default_host_threads()
+    in_use = dec.host_threads_in_use(4)
 
     def host_step(xt, zt, elem):
         tot, off = np.zeros(q.NUM_COUNTERS, np.uint64), 0
@@ -373,8 +376,9 @@ def run_native(args):
         return allreduce_max(time.perf_counter() - t0, "cuda"), out
 
     e2e_raw_s, raw_counters = time_host(xh, zh, 4, 0)
-    e2e_s, e2e_counters = time_host(xh, zh, 4, host_threads)
+    e2e_packed_s, e2e_counters = time_host(xh, zh, 4, host_threads)
     assert np.array_equal(raw_counters, e2e_counters)
+    e2e_s = e2e_packed_s if in_use > 0 else e2e_raw_s
     # same patterns as step 0 of the device-resident run => same counters (checked on every rank)
     chk = np.stack(device_step(0)).sum(axis=0)
     assert np.array_equal(chk, e2e_counters), "host-buffer path and device-generated path disagree"
@@ -394,7 +398,8 @@ def run_native(args):
     # qldpc_get_statistics_depolarizing (what GetStatistics(W, COUNT, p, MAXIT) is in the reference's driver,
     # main.cu:101): scalars in, counters out, errors generated on the device -- timed on the host clock.
     xb, zb = xh.to(torch.uint8).pin_memory(), zh.to(torch.uint8).pin_memory()
-    e2e_u8_s, u8_counters = time_host(xb, zb, 1, host_threads)
+    e2e_u8_s, u8_counters = time_host(xb, zb, 1, -1)  # library default for byte rows
+    in_use8 = dec.host_threads_in_use(1)
     assert np.array_equal(chk, u8_counters)
     barrier()
     t0 = time.perf_counter()
@@ -481,13 +486,15 @@ def run_native(args):
             "kernel_ms_per_step": {k: v / args.steps for k, v in kms.items()},
             "launch": {"x": info[0], "z": info[1]},
             "e2e": {"value": F * n_gpus * args.steps / e2e_s, "unit": "frames/s",
-                    "h2d_bytes_per_step": 2 * F * code_nw * 4, "d2h_bytes_per_step": q.NUM_COUNTERS * 8 * len(segs),
-                    "host_buffer_bytes_per_step": host_bytes, "host_threads": host_threads,
+                    "h2d_bytes_per_step": 2 * F * code_nw * 4 if in_use > 0 else host_bytes,
+                    "d2h_bytes_per_step": q.NUM_COUNTERS * 8 * len(segs),
+                    "host_buffer_bytes_per_step": host_bytes, "host_threads": in_use,
+                    "method": "host_packed (%d threads per rank)" % in_use if in_use > 0 else "raw_rows_over_link",
                     "api": "qldpc_get_stats_from_errors_i32 (DecoderGPU::GetStats layout, pinned host int32)",
-                    "note": "the reference's layout spends one int32 per qubit (%d B per frame); the library's host threads "
-                            "pack the rows to bits before the copy, the same way at every rank count; "
-                            "raw_rows_over_link = the same call with host packing off (the int32 rows cross the link); "
-                            "u8_patterns and device_generated show the other two entry points" % (2 * n * 4),
+                    "note": "the reference's layout spends one int32 per qubit (%d B per frame); `value` is the library's "
+                            "default marshalling on this box (`method`); host_packed and raw_rows_over_link are both timed "
+                            "at every rank count, so either series can be followed on its own; u8_patterns and "
+                            "device_generated show the other two entry points" % (2 * n * 4),
                     "ms_per_step": 1e3 * e2e_s / args.steps,
                     "vs_device_value": (F * n_gpus * args.steps / e2e_s) / value,
                     "host_mem_roofline": {"bound": "host memory read bandwidth", "unit": "GB/s",
@@ -498,11 +505,15 @@ def run_native(args):
                                           "peak_source": "measured: streaming read of the same pinned buffers by the same "
                                                          "%d threads per rank, all %d ranks at once "
                                                          "(qldpc_debug_host_read_gbs)" % (host_threads, n_gpus)},
+                    "host_packed": {"value": F * n_gpus * args.steps / e2e_packed_s, "unit": "frames/s",
+                                    "h2d_bytes_per_step": 2 * F * code_nw * 4, "host_threads": host_threads},
                     "raw_rows_over_link": {"value": F * n_gpus * args.steps / e2e_raw_s, "unit": "frames/s",
                                            "h2d_bytes_per_step": host_bytes, "host_threads": 0},
                     "u8_patterns": {"value": F * n_gpus * args.steps / e2e_u8_s, "unit": "frames/s",
-                                    "h2d_bytes_per_step": 2 * F * code_nw * 4,
-                                    "host_buffer_bytes_per_step": 2 * F * n, "host_threads": host_threads,
+                                    "h2d_bytes_per_step": 2 * F * code_nw * 4 if in_use8 > 0 else 2 * F * n,
+                                    "host_buffer_bytes_per_step": 2 * F * n, "host_threads": in_use8,
+                                    "method": "host_packed (%d threads per rank)" % in_use8 if in_use8 > 0
+                                              else "raw_rows_over_link",
                                     "vs_device_value": (F * n_gpus * args.steps / e2e_u8_s) / value,
                                     "api": "qldpc_get_stats_from_errors_u8"},
                     "device_generated": {"value": F * n_gpus * args.steps / e2e_gs_s, "unit": "frames/s",

@@ -71,6 +71,7 @@ def load_library():
     L.qldpc_decoder_configure.argtypes = [vp, i32, i32, i32, i32]
     L.qldpc_decoder_set_host_threads.argtypes = [vp, i32]
     L.qldpc_decoder_launch_info.argtypes = [vp, i32, vp]
+    L.qldpc_decoder_host_threads_in_use.argtypes = [vp, i32]
     L.qldpc_decode_batch.argtypes = [vp, vp, vp, i64, f32, i32, vp, vp, vp, vp]
     L.qldpc_decode_batch_device.argtypes = [vp, vp, vp, i64, f32, i32, vp, vp, vp, vp]
     L.qldpc_get_statistics_weightw.argtypes = [vp, i32, i64, f32, i32, u32, vp, vp, vp]
@@ -257,6 +258,10 @@ class Decoder:
     def set_host_threads(self, threads):
         """Worker threads that pack host rows before the H2D copy (-1 default, 0 = copy raw rows, pack on device)."""
         _check(self._lib.qldpc_decoder_set_host_threads(self.h, threads))
+
+    def host_threads_in_use(self, elem=4):
+        """Threads the host-buffer entry points use for rows of `elem`-byte elements (0 = raw rows over the link)."""
+        return _check(self._lib.qldpc_decoder_host_threads_in_use(self.h, elem))
 
     def launch_info(self, side):
         out = np.zeros(8, np.int32)

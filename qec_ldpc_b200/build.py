@@ -37,12 +37,19 @@ def _env():
     return env
 
 
+# what the last build_all() did: {"library": "compiled" | "up to date", "cli": ...} -- __graft_entry__.build() prints it,
+# so a log shows whether the nvcc step was exercised or the prebuilt, mtime-fresh binaries were reused
+LAST_BUILD = {}
+
+
 def build_library(force=False, verbose=False):
     os.makedirs(LIBDIR, exist_ok=True)
     srcs = [os.path.join(CSRC, s) for s in LIB_SOURCES]
     deps = srcs + [os.path.join(CSRC, f) for f in os.listdir(CSRC) if f.endswith((".h", ".cuh"))]
     deps.append(os.path.join(ROOT, "include", "qldpc_b200.h"))
+    LAST_BUILD["library"] = "up to date"
     if force or _stale(LIB, deps):
+        LAST_BUILD["library"] = "compiled (%d translation units, nvcc sm_100a)" % len(srcs)
         objs = []
         procs = []
         for s in srcs:
@@ -63,7 +70,9 @@ def build_cli(force=False):
     if not os.path.exists(src):
         return None
     deps = [src] + [os.path.join(HERE, "cpp", f) for f in os.listdir(os.path.join(HERE, "cpp"))]
+    LAST_BUILD["cli"] = "up to date"
     if force or _stale(CLI, deps + [LIB]):
+        LAST_BUILD["cli"] = "compiled"
         cmd = ["g++", "-O2", "-std=c++17", "-I", os.path.join(ROOT, "include"), "-I", os.path.join(HERE, "cpp"), src,
                "-o", CLI, "-L", LIBDIR, "-lqldpc_b200", "-Wl,-rpath,$ORIGIN", "-pthread"]
         subprocess.run(cmd, check=True, env=_env())

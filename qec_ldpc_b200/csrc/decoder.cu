@@ -90,6 +90,7 @@ struct qldpc_decoder {
   // straggler tail of one kernel overlaps the start of the other
   cudaStream_t side_stream = nullptr;
   cudaEvent_t ev_fork = nullptr, ev_join = nullptr;
+  bool overlap_sides = false;  // set by the sliced / small-batch entry points for the duration of the call
   uint8_t* small_pin = nullptr;  // pinned staging of the low-latency Decode path
   size_t small_pin_bytes = 0;
   // the low-latency path replays a captured CUDA graph when the call repeats the previous one's shape (a per-frame
@@ -202,6 +203,12 @@ int64_t slice_frames(int index, int64_t max_slice) {
   return std::min<int64_t>(s, max_slice);
 }
 
+struct OverlapScope {  // X and Z side by side for the calls made while one of these is alive
+  qldpc_decoder* d;
+  explicit OverlapScope(qldpc_decoder* d_) : d(d_) { d->overlap_sides = true; }
+  ~OverlapScope() { d->overlap_sides = false; }
+};
+
 // Waits for everything a pipelined call may still have in flight (error exits: the caller's buffers and the pinned
 // staging must not be touched by asynchronous copies after the call has returned).
 void quiesce(qldpc_decoder* d) {
@@ -243,9 +250,20 @@ int ensure_pin(qldpc_decoder* d, size_t words) {
   return QLDPC_OK;
 }
 
+// Host threads the host-buffer entry points use for rows of `elem`-byte elements (0 = raw rows over the link, packed on
+// the device).  An explicit qldpc_decoder_set_host_threads setting is taken as given.  By default the rows are packed
+// on the host when enough cores are available to this process to outrun the raw copy: 6 for int32 rows (raw rows are
+// bound by the link at 4 bytes per bit), 8 for byte rows (the link carries those at the decode rate; below 8 threads
+// the DMA engines read host memory faster than the threads do).  Measured: profiles/r2/host_pack_e2e.jsonl.
+int host_threads_for(const qldpc_decoder* d, int elem) {
+  if (d->host_threads >= 0) return d->host_threads;
+  const int want = default_host_threads();
+  return want >= (elem == 4 ? 6 : 8) ? want : 0;
+}
+
 // The host packer, or null when host-side packing is switched off.
-HostPacker* host_packer(qldpc_decoder* d) {
-  const int want = d->host_threads < 0 ? default_host_threads() : d->host_threads;
+HostPacker* host_packer(qldpc_decoder* d, int elem) {
+  const int want = host_threads_for(d, elem);
   if (want <= 0) return nullptr;
   if (!d->packer || d->packer->threads() != want) d->packer.reset(new HostPacker(want));
   return d->packer.get();
@@ -353,7 +371,9 @@ int resolve_config(qldpc_decoder* d, int side) {
 // Which range tests the kernel's branch-free division needs outside the `last` iteration (bp_kernel.cuh:div_fast).
 // A numerator is prior * (dv-1 check-to-variable messages), each 0 or >= 2^-25; a denominator adds
 // (1-prior) * (dv-1 complements), each 0 or >= 2^-24.  If the smallest non-zero value already clears the
-// threshold the test can never fire and is compiled out.
+// threshold the test can never fire and is compiled out (0).  If a numerator could fall below 2^-100 while neither
+// chain can leave the normal range (>= 2^-126), the kernel runs both chains scaled by 2^64 instead of testing (1: exact,
+// see var_phase).  Otherwise both tests stay in (3).
 int division_guard(float prior, int dv) {
   if (!(prior > 0.0f && prior < 1.0f)) return 3;
   const int nf = dv - 1;
@@ -372,9 +392,10 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
   if (nf <= 0) return QLDPC_OK;
   const float prior = 2.0f / 3.0f * errorProbability;  // DecoderCPU.h:259, same float expression
   CU_TRY(cudaMemsetAsync(d->queues, 0, 2 * sizeof(unsigned int), d->stream));
-  // Slices and small batches: the Z side runs beside the X side on a second stream (its CTAs move in as the X side's
-  // drain); full-size launches run back to back, where the tail is negligible and per-kernel timing stays clean.
-  const bool overlap = only_side < 0 && nf <= (1 << 18) && !trace_q && !trace_r && !d->s[0].use_global &&
+  // Slices and small batches (the host-buffer entry points): the Z side runs beside the X side on a second stream (its
+  // CTAs move in as the X side's drain); the device-resident statistics calls launch back to back -- their launches
+  // are large, the tail is negligible there, and the per-kernel timing stays clean.
+  const bool overlap = d->overlap_sides && only_side < 0 && !trace_q && !trace_r && !d->s[0].use_global &&
                        !d->s[1].use_global && ensure_side_stream(d) == QLDPC_OK;
   if (overlap) {
     CU_TRY(cudaEventRecord(d->ev_fork, d->stream));
@@ -766,6 +787,11 @@ int qldpc_decoder_set_host_threads(qldpc_decoder* dec, int threads) {
 
 int qldpc_default_host_threads(void) { return default_host_threads(); }
 
+int qldpc_decoder_host_threads_in_use(qldpc_decoder* dec, int elem_size) {
+  if (!dec || (elem_size != 1 && elem_size != 4)) return fail(QLDPC_ERR_ARG, "bad argument");
+  return host_threads_for(dec, elem_size);
+}
+
 int qldpc_decoder_launch_info(qldpc_decoder* dec, int side, int32_t out[8]) {
   if (!dec || !out || side < 0 || side > 1) return fail(QLDPC_ERR_ARG, "bad argument");
   const DevSide& s = dec->s[side];
@@ -920,6 +946,7 @@ int qldpc_decode_batch(qldpc_decoder* dec, const uint8_t* synX, const uint8_t* s
   if (rc) return rc;
   if (!synX || !synZ || !outX || !outZ || !outFlags) return fail(QLDPC_ERR_ARG, "null buffer");
   if (nframes == 0) return QLDPC_OK;
+  OverlapScope overlap(dec);
   if (nframes <= std::min<int64_t>(kSmallBatch, dec->chunk))
     rc = decode_small(dec, synX, synZ, (int)nframes, errorProbability, maxIterations, outX, outZ, outFlags, outIters);
   else
@@ -943,7 +970,7 @@ static int decode_batch_impl(qldpc_decoder* dec, const uint8_t* synX, const uint
   qldpc_decoder* d = dec;
   const int n = d->n, mX = d->s[0].m, mZ = d->s[1].m;
   const int64_t slice = std::min<int64_t>(std::min<int64_t>(d->chunk, kPipeFrames), std::max<int64_t>(nframes, 1));
-  if (HostPacker* hp = host_packer(d)) {
+  if (HostPacker* hp = host_packer(d, 1)) {
     // Host-packed variant of the same pipeline: syndromes are packed on the host before the H2D copy and the
     // corrections come back as packed words that the host threads expand to one byte per bit, so the link carries
     // 1/8 of the bytes in both directions and pageable user buffers cost nothing extra.  While the device works on
@@ -1102,6 +1129,8 @@ static int weightw_impl(qldpc_decoder* dec, int errorWeight, int64_t numErrors, 
 int qldpc_get_statistics_weightw(qldpc_decoder* dec, int errorWeight, int64_t numErrors, float errorProbability,
                                  int maxIterations, uint32_t seed, uint64_t* counters, uint8_t* perFrameFlags,
                                  uint32_t* perFrameIters) {
+  if (!dec) return fail(QLDPC_ERR_ARG, "null decoder");
+  OverlapScope overlap(dec);
   const int rc = weightw_impl(dec, errorWeight, numErrors, errorProbability, maxIterations, seed, counters, perFrameFlags,
                               perFrameIters);
   if (rc && dec) {
@@ -1128,7 +1157,12 @@ static int weightw_impl(qldpc_decoder* dec, int errorWeight, int64_t numErrors, 
   rc = ensure_pipeline(d);
   if (rc) return rc;
   WeightWGenerator gen(seed, n, errorWeight);  // DecoderCPU.h:394
-  HostPacker* pool = host_packer(d);
+  HostPacker* pool = host_packer(d, 4);
+  std::unique_ptr<HostPacker> own_pool;  // the weight-W generator always needs workers for its mapping stage
+  if (!pool) {
+    own_pool.reset(new HostPacker(std::max(1, default_host_threads())));
+    pool = own_pool.get();
+  }
   CU_TRY(cudaMemsetAsync(d->counters, 0, QLDPC_NUM_COUNTERS * sizeof(unsigned long long), d->stream));
   int i = 0;
   for (int64_t off = 0; off < numErrors; off += slice, ++i) {
@@ -1164,6 +1198,8 @@ static int stats_from_errors_impl(qldpc_decoder* d, const void* xErrors, const v
 static int stats_from_errors(qldpc_decoder* d, const void* xErrors, const void* zErrors, int elem, int64_t numErrors,
                              float errorProbability, int maxIterations, uint64_t* counters, uint8_t* perFrameFlags,
                              uint32_t* perFrameIters) {
+  if (!d) return fail(QLDPC_ERR_ARG, "null decoder");
+  OverlapScope overlap(d);
   const int rc = stats_from_errors_impl(d, xErrors, zErrors, elem, numErrors, errorProbability, maxIterations, counters,
                                         perFrameFlags, perFrameIters);
   if (rc && d) {
@@ -1183,7 +1219,7 @@ static int stats_from_errors_impl(qldpc_decoder* d, const void* xErrors, const v
   const int n = d->n;
   const size_t row = (size_t)n * elem;
   const int64_t slice = std::min<int64_t>(std::min<int64_t>(d->chunk, kPipeFrames), std::max<int64_t>(numErrors, 1));
-  if (HostPacker* hp = host_packer(d)) {
+  if (HostPacker* hp = host_packer(d, elem)) {
     // Host-packed pipeline: while the device decodes slice i the host threads pack slice i+1 into pinned memory;
     // only nw words per row cross the link (1/32 of the int layout), through a double-buffered device stage.
     const int nw = d->nw;
