@@ -1,7 +1,8 @@
 // Explicit instantiation of the BP tile kernel for one (check degree, variable degree) shape: tile widths 1/2/4 and
 // the three division-guard variants.  One translation unit per shape so that nvcc builds them in parallel.
 // A shape may add instantiations with the number of checks as a compile-time constant (QLDPC_DEFINE_SHAPE_M): the
-// check-phase addresses of such a kernel are immediates; it is picked when the code's check count matches.
+// check-phase addresses of such a kernel are immediates and its phase loops are unrolled for 128 threads per CTA; it is
+// picked when the code's check count and the launch shape match.
 #pragma once
 #include "bp_kernel.cuh"
 
@@ -23,11 +24,11 @@ BpKernel bp_kernel_for(int vec, int guard) {
 }  // namespace qldpc
 
 #define QLDPC_DEFINE_SHAPE(DC, DV) \
-  namespace qldpc { BpKernel bp_shape_##DC##_##DV(int vec, int guard, int) { return bp_kernel_for<DC, DV, 0>(vec, guard); } }
+  namespace qldpc { BpKernel bp_shape_##DC##_##DV(int vec, int guard, int, int) { return bp_kernel_for<DC, DV, 0>(vec, guard); } }
 #define QLDPC_DEFINE_SHAPE_M(DC, DV, M)                                       \
   namespace qldpc {                                                           \
-  BpKernel bp_shape_##DC##_##DV(int vec, int guard, int m) {                  \
-    if (m == M) return bp_kernel_for<DC, DV, M>(vec, guard);                  \
+  BpKernel bp_shape_##DC##_##DV(int vec, int guard, int m, int threads) {     \
+    if (m == M && threads == 128) return bp_kernel_for<DC, DV, M>(vec, guard); \
     return bp_kernel_for<DC, DV, 0>(vec, guard);                              \
   }                                                                           \
   }

@@ -31,7 +31,7 @@ static int sm_count() {
 }
 // one translation unit per shape (bp_shape_<dc>_<dv>.cu)
 #define QLDPC_SHAPES(X) X(6, 3) X(10, 4) X(10, 5) X(8, 4) X(8, 3) X(12, 6) X(10, 3) X(12, 3) X(12, 4) X(12, 5) X(4, 2) X(6, 2) X(8, 2) X(10, 2) X(12, 2)
-#define QLDPC_DECL(DC, DV) BpKernel bp_shape_##DC##_##DV(int vec, int guard, int m);
+#define QLDPC_DECL(DC, DV) BpKernel bp_shape_##DC##_##DV(int vec, int guard, int m, int threads);
 QLDPC_SHAPES(QLDPC_DECL)
 #undef QLDPC_DECL
 
@@ -42,10 +42,10 @@ static bool specialization_enabled() {
   return !(e && e[0] && e[0] != '0');
 }
 
-static BpKernel lookup_kernel(int dc, int dv, int vec, int guard, int m) {
+static BpKernel lookup_kernel(int dc, int dv, int vec, int guard, int m, int threads = 0) {
   if (!specialization_enabled()) m = 0;
 #define QLDPC_CASE(DC, DV) \
-  if (dc == DC && dv == DV) return bp_shape_##DC##_##DV(vec, guard, m);
+  if (dc == DC && dv == DV) return bp_shape_##DC##_##DV(vec, guard, m, threads);
   QLDPC_SHAPES(QLDPC_CASE)
 #undef QLDPC_CASE
   return nullptr;
@@ -68,10 +68,11 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   // divide evenly among the CTA's warps.  Wider tiles win ties (fewer shared-memory instructions per edge-update).
   auto regs_of = [&](int v) {
     int r = 0;
-    for (int guard : {0, 1, 3}) {
-      cudaFuncAttributes fa;
-      if (cudaFuncGetAttributes(&fa, lookup_kernel(dc, dv, v, guard, m)) == cudaSuccess) r = std::max(r, fa.numRegs);
-    }
+    for (int guard : {0, 1, 3})
+      for (int thr : {0, 128}) {  // generic instantiation and, where there is one, the one specialised for this code
+        cudaFuncAttributes fa;
+        if (cudaFuncGetAttributes(&fa, lookup_kernel(dc, dv, v, guard, m, thr)) == cudaSuccess) r = std::max(r, fa.numRegs);
+      }
     cudaGetLastError();
     return std::max(r, 32);
   };
@@ -116,16 +117,17 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   if (smem > smem_optin) { *why = kBadCfg; return false; }
   // The attribute is a per-kernel ceiling shared by every decoder of the process (several codes can use the same
   // instantiation with different tile sizes), so it is raised to the device limit rather than to this tile's size.
-  for (int guard : {0, 1, 3}) {
-    if (cudaFuncSetAttribute(lookup_kernel(dc, dv, vec, guard, m), cudaFuncAttributeMaxDynamicSharedMemorySize,
-                             smem_optin) != cudaSuccess) {
-      cudaGetLastError();
-      *why = kNoFit;
-      return false;
+  for (int guard : {0, 1, 3})
+    for (int thr : {0, 128}) {
+      if (cudaFuncSetAttribute(lookup_kernel(dc, dv, vec, guard, m, thr), cudaFuncAttributeMaxDynamicSharedMemorySize,
+                               smem_optin) != cudaSuccess) {
+        cudaGetLastError();
+        *why = kNoFit;
+        return false;
+      }
     }
-  }
   const int regs = regs_of(vec);
-  BpKernel k = lookup_kernel(dc, dv, vec, 3, m);
+  BpKernel k = lookup_kernel(dc, dv, vec, 3, m, threads);
   if (threads % 32 || threads < 32 || threads > kMaxT) { *why = kBadCfg; return false; }
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem) != cudaSuccess || occ < 1) {
@@ -145,7 +147,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
 }
 
 cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, int guard, cudaStream_t st) {
-  BpKernel k = lookup_kernel(dc, dv, cfg.vec, guard, args.m);
+  BpKernel k = lookup_kernel(dc, dv, cfg.vec, guard, args.m, cfg.threads);
   if (!k) return cudaErrorInvalidDeviceFunction;
   const int tiles = (nframes + cfg.vec - 1) / cfg.vec;
   const int grid = std::max(1, std::min(cfg.grid, tiles));
