@@ -47,6 +47,10 @@ struct DevSide {
   int m = 0, dc = 0, dv = 0, E = 0, mw = 0;
   uint16_t* vrow = nullptr;  // [dv][n]
   uint16_t* vchk = nullptr;  // [dv][n] check index of the k-th edge of variable v (CSC)
+  // [dv][L] circulant exponents of a quasi-cyclic side: the BP kernel generates its row table from them on the device
+  // (the syndrome kernels keep the CSC table: two instructions per index against eight for the closed form)
+  int32_t* hexp = nullptr;
+  int P = 0, L = 0;
   BpLaunch cfg, user;        // resolved configuration / user overrides
   bool cfg_ok = false;
   std::string cfg_err;
@@ -122,7 +126,7 @@ struct qldpc_decoder {
   ~qldpc_decoder() {
     cudaSetDevice(device);
     for (int i = 0; i < 2; ++i) {
-      cudaFree(s[i].vrow); cudaFree(s[i].vchk); cudaFree(s[i].gvrow); cudaFree(s[i].gcvar);
+      cudaFree(s[i].vrow); cudaFree(s[i].vchk); cudaFree(s[i].hexp); cudaFree(s[i].gvrow); cudaFree(s[i].gcvar);
       cudaFree(s[i].gmsg); cudaFree(s[i].gbytes); cudaFree(s[i].gwords);
       if (s[i].ghost_done) cudaFreeHost(s[i].ghost_done);
     }
@@ -412,6 +416,7 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
     a.flags = side ? sfZ : sfX;
     a.iters = side ? itZ : itX;
     a.vrow = s.vrow;
+    a.hexp = s.hexp; a.P = s.P; a.L = s.L;
     a.queue = d->queues + side;
     a.m = s.m; a.n = d->n; a.mw = s.mw; a.nw = d->nw;
     a.nframes = nf;
@@ -719,6 +724,13 @@ int qldpc_decoder_create(const qldpc_code* code, int device_ordinal, int max_fra
     D_TRY(dev_alloc(s.vchk, vchk.size()));
     D_TRY(cudaMemcpy(s.vrow, vrow.data(), vrow.size() * 2, cudaMemcpyHostToDevice));
     D_TRY(cudaMemcpy(s.vchk, vchk.data(), vchk.size() * 2, cudaMemcpyHostToDevice));
+    if (!t.hexp.empty() && (int)t.hexp.size() == t.dv * d->code.L && t.m == t.dv * d->code.P) {
+      // quasi-cyclic side: the kernels generate their index tables from the exponents instead of reading them
+      D_TRY(dev_alloc(s.hexp, t.hexp.size()));
+      D_TRY(cudaMemcpy(s.hexp, t.hexp.data(), t.hexp.size() * sizeof(int32_t), cudaMemcpyHostToDevice));
+      s.P = d->code.P;
+      s.L = d->code.L;
+    }
     resolve_config(d, side);  // failure is reported when the side is first used
   }
   const size_t F = (size_t)d->chunk;
