@@ -1,5 +1,4 @@
-// See host_pack.h.  The inner loops have an AVX-512 form (vptestmd / vptestmb straight into mask registers, software
-// prefetch ahead of the stream), an AVX2 form (32 source elements per step) and a portable form, selected at run time;
+// See host_pack.h.  The inner loops have an AVX-512 form (vptestmd / vptestmb straight into mask registers), an AVX2 form (32 source elements per step) and a portable form, selected at run time;
 // all produce the same words.
 #include "host_pack.h"
 
@@ -84,8 +83,9 @@ __attribute__((target("avx2"))) static void pack_rows_avx2_u8(const uint8_t* src
 }
 
 // AVX-512: 16 ints (or 64 bytes) per test instruction, result lands in a mask register.  The loads are ordinary
-// (write-back memory: a non-temporal load is only a hint there); a software prefetch a few lines ahead keeps more
-// requests in flight per core than the hardware prefetcher alone, which is what a memory-bound single thread needs.
+// (write-back memory: a non-temporal load is only a hint there) and there is NO software prefetch: measured on the
+// B200 hosts, a prefetchnta ahead of the stream costs a third of the aggregate rate as soon as many threads stream at
+// once (32 threads: 190 GB/s without, 128 GB/s with; AVX2: 172 GB/s -- tools/bench_host_pack_ranks.py).
 __attribute__((target("avx512f,avx512bw"))) static void pack_rows_avx512_i32(const int32_t* src, int64_t r0, int64_t r1,
                                                                              int cols, int words, uint32_t* dst) {
   const int full = cols / 32;
@@ -93,8 +93,6 @@ __attribute__((target("avx512f,avx512bw"))) static void pack_rows_avx512_i32(con
     const int32_t* p = src + r * cols;
     uint32_t* d = dst + r * words;
     for (int w = 0; w < full; ++w, p += 32) {
-      _mm_prefetch(reinterpret_cast<const char*>(p) + 1536, _MM_HINT_NTA);
-      _mm_prefetch(reinterpret_cast<const char*>(p) + 1600, _MM_HINT_NTA);
       const __m512i a = _mm512_loadu_si512(p), b = _mm512_loadu_si512(p + 16);
       d[w] = (uint32_t)_mm512_test_epi32_mask(a, a) | ((uint32_t)_mm512_test_epi32_mask(b, b) << 16);
     }
@@ -110,7 +108,6 @@ __attribute__((target("avx512f,avx512bw"))) static void pack_rows_avx512_u8(cons
     uint32_t* d = dst + r * words;
     int w = 0;
     for (int k = 0; k < full; ++k, p += 64, w += 2) {
-      _mm_prefetch(reinterpret_cast<const char*>(p) + 1024, _MM_HINT_NTA);
       const __m512i a = _mm512_loadu_si512(p);
       const uint64_t m = (uint64_t)_mm512_test_epi8_mask(a, a);
       d[w] = (uint32_t)m;
@@ -125,7 +122,6 @@ __attribute__((target("avx512f,avx512bw"))) static uint64_t read_avx512(const ui
   __m512i acc = _mm512_setzero_si512();
   size_t i = 0;
   for (; i + 64 <= bytes; i += 64) {
-    _mm_prefetch(reinterpret_cast<const char*>(p + i) + 1536, _MM_HINT_NTA);
     acc = _mm512_or_si512(acc, _mm512_loadu_si512(p + i));
   }
   return (uint64_t)_mm512_reduce_or_epi64(acc);
@@ -169,9 +165,19 @@ static void unpack_rows_portable(const uint32_t* src, int64_t r0, int64_t r1, in
   }
 }
 
+// QLDPC_HOST_ISA=avx2|portable in the environment caps the instruction set of the packers (measurement knob)
+static int isa_cap() {
+  static const int cap = [] {
+    const char* e = std::getenv("QLDPC_HOST_ISA");
+    if (!e) return 2;
+    return !std::strcmp(e, "portable") ? 0 : !std::strcmp(e, "avx2") ? 1 : 2;
+  }();
+  return cap;
+}
+
 static bool have_avx512() {
 #ifdef QLDPC_X86
-  static const bool ok = __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
+  static const bool ok = isa_cap() >= 2 && __builtin_cpu_supports("avx512f") && __builtin_cpu_supports("avx512bw");
   return ok;
 #else
   return false;
@@ -180,7 +186,7 @@ static bool have_avx512() {
 
 static bool have_avx2() {
 #ifdef QLDPC_X86
-  static const bool ok = __builtin_cpu_supports("avx2");
+  static const bool ok = isa_cap() >= 1 && __builtin_cpu_supports("avx2");
   return ok;
 #else
   return false;
