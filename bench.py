@@ -338,7 +338,7 @@ def run_native(args):
     # read are all inside the timed region.  The call has two ways to marshal the rows: pack them to bits with host
     # threads before the copy, or copy the raw rows and pack on the device.  BOTH are timed every time, at every rank
     # count (host_packed: min(16, cores / local ranks) threads; raw_rows_over_link: threads = 0); `value` is the one the
-    # library picks by default on this box (packing needs >= 6 threads per rank to beat the raw copy of int32 rows),
+    # library picks by default on this box (packing needs >= 10 threads per rank to beat the raw copy of int32 rows),
     # named in `method`.
     n = code.n
     code_nw = (n + 31) // 32

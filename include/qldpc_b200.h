@@ -126,7 +126,7 @@ int qldpc_decoder_configure(qldpc_decoder* dec, int side, int frames_per_tile, i
 /* Host-buffer entry points (qldpc_get_stats_from_errors_*, qldpc_decode_batch) convert the reference's
  * one-element-per-bit rows to packed words on the host with `threads` worker threads, so that 1/32 (int) or 1/8 (byte)
  * of the bytes cross the host-device link.  threads < 0: default (environment QLDPC_HOST_THREADS, else
- * min(16, hardware threads / processes on this host as announced by the launcher); with fewer than 6 (int32 rows) or
+ * min(16, hardware threads / processes on this host as announced by the launcher); with fewer than 10 (int32 rows) or
  * 8 (byte rows) the raw rows are copied instead, see qldpc_decoder_host_threads_in_use); 0: off -- raw rows
  * are copied and packed on the device.  Batches of at most 2048 frames of qldpc_decode_batch take a low-latency path
  * without host threads.  Marshalling only: the decode itself never runs on the host. */
@@ -134,7 +134,7 @@ int qldpc_decoder_set_host_threads(qldpc_decoder* dec, int threads);
 int qldpc_default_host_threads(void); /* min(16, cores / ranks) for this process */
 /* Threads the host-buffer entry points will use for rows of elem_size-byte elements (1 or 4) with the current setting;
  * 0 = the raw rows are copied and packed on the device.  With the default setting the library packs on the host only
- * when that beats the raw copy: at least 6 threads for int32 rows, at least 8 for byte rows. */
+ * when that beats the raw copy: at least 10 threads for int32 rows, at least 8 for byte rows. */
 int qldpc_decoder_host_threads_in_use(qldpc_decoder* dec, int elem_size);
 /* Launch geometry in use: out[0..7] = vec (-1: global-memory path), threads, ctas_per_sm, grid, dyn_smem_bytes, regs,
  * SM count, frames per launch. */

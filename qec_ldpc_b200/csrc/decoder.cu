@@ -256,13 +256,17 @@ int ensure_pin(qldpc_decoder* d, size_t words) {
 
 // Host threads the host-buffer entry points use for rows of `elem`-byte elements (0 = raw rows over the link, packed on
 // the device).  An explicit qldpc_decoder_set_host_threads setting is taken as given.  By default the rows are packed
-// on the host when enough cores are available to this process to outrun the raw copy: 6 for int32 rows (raw rows are
-// bound by the link at 4 bytes per bit), 8 for byte rows (the link carries those at the decode rate; below 8 threads
-// the DMA engines read host memory faster than the threads do).  Measured: profiles/r2/host_pack_e2e.jsonl.
+// on the host when this process has enough cores to itself to outrun the raw copy:
+//  * int32 rows (4 bytes per bit): the raw copy is bound by the GPU's own host link (about 10.5 M frames/s per GPU for
+//    n = 610) and scales with the number of GPUs until host DRAM saturates, whereas packing is bound by what the
+//    host's cores can stream in total (140-190 GB/s on the 32-core B200 hosts, i.e. 29-39 M frames/s per BOX).  With
+//    one or two ranks per box (>= 10 threads each) packing wins; from four ranks on the raw copy does.
+//  * byte rows: the link carries them at the decode rate; packing only helps with >= 8 threads.
+// Measured: profiles/r2/host_pack_e2e.jsonl, host_pack_ranks.jsonl, bench_C2_{1,2,4,8}gpu.json (both series in every line).
 int host_threads_for(const qldpc_decoder* d, int elem) {
   if (d->host_threads >= 0) return d->host_threads;
   const int want = default_host_threads();
-  return want >= (elem == 4 ? 6 : 8) ? want : 0;
+  return want >= (elem == 4 ? 10 : 8) ? want : 0;
 }
 
 // The host packer, or null when host-side packing is switched off.
