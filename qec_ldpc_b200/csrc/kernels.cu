@@ -68,7 +68,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   // divide evenly among the CTA's warps.  Wider tiles win ties (fewer shared-memory instructions per edge-update).
   auto regs_of = [&](int v) {
     int r = 0;
-    for (int guard : {0, 1, 3})
+    for (int guard : {0, 1, 3, 4, 5, 7})
       for (int thr : {0, 128}) {  // generic instantiation and, where there is one, the one specialised for this code
         cudaFuncAttributes fa;
         if (cudaFuncGetAttributes(&fa, lookup_kernel(dc, dv, v, guard, m, thr)) == cudaSuccess) r = std::max(r, fa.numRegs);
@@ -117,7 +117,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   if (smem > smem_optin) { *why = kBadCfg; return false; }
   // The attribute is a per-kernel ceiling shared by every decoder of the process (several codes can use the same
   // instantiation with different tile sizes), so it is raised to the device limit rather than to this tile's size.
-  for (int guard : {0, 1, 3})
+  for (int guard : {0, 1, 3, 4, 5, 7})
     for (int thr : {0, 128}) {
       if (cudaFuncSetAttribute(lookup_kernel(dc, dv, vec, guard, m, thr), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                smem_optin) != cudaSuccess) {
@@ -147,6 +147,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
 }
 
 cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, int guard, cudaStream_t st) {
+  if (args.trace_q || args.trace_r) guard += 4;  // the same instantiation with the message taps compiled in
   BpKernel k = lookup_kernel(dc, dv, cfg.vec, guard, args.m, cfg.threads);
   if (!k) return cudaErrorInvalidDeviceFunction;
   const int tiles = (nframes + cfg.vec - 1) / cfg.vec;
