@@ -194,6 +194,27 @@ def test_zero_noise_and_saturated_noise(oracle, decoders):
     assert int(z[1]) == 0 and int(z[3]) == 500 and int(z[9]) == 500  # nothing to correct, one iteration each
 
 
+@pytest.mark.parametrize("code", ["C1", "C2"])
+@pytest.mark.parametrize("p", [1.5, 1.2, 0.0])
+def test_nan_messages_decide_like_the_reference(oracle, decoders, code, p):
+    """prior = 2/3 p >= 1 (or 0) drives messages to 0/0: a NaN message compares false in the hard decision
+    (DecoderCPU.h:354-373) and counts as converged (:231-246).  Decisions, flags and iteration counts per frame."""
+    gc, dec = decoders(code)
+    oc = ocode(oracle, code, gc)
+    nf = 300
+    x, z = oc.depolarizing_bulk(11, 0, nf, 0.04)  # ordinary error patterns, decoded with the extreme prior
+    x[0] = 0
+    z[0] = 0
+    want = oc.run_frames(x, z, p, 30, 0, want_out=True)
+    sx = np.stack([oc.syndrome(0, x[f]) for f in range(nf)])
+    sz = np.stack([oc.syndrome(1, z[f]) for f in range(nf)])
+    ox, oz, fl, it = dec.decode_batch(sx, sz, p, 30)
+    assert np.array_equal(ox, want["outX"]) and np.array_equal(oz, want["outZ"])
+    assert np.array_equal(np.asarray(it).reshape(nf, 2), want["iters"])
+    st = dec.get_stats_from_errors(x, z, p, 30, per_frame=True)
+    assert np.array_equal(st["flags"] & 63, want["flags"] & 63) and np.array_equal(st["counters"], want["counters"])
+
+
 def test_tile_width_and_launch_shape_do_not_change_results(qldpc):
     gc = qldpc.Code.qc(*CODES["C2"])
     dec = qldpc.Decoder(gc, 0, 1 << 14)
