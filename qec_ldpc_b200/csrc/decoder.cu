@@ -352,7 +352,7 @@ int resolve_config(qldpc_decoder* d, int side) {
   BpLaunch cfg = s.user;
   const char* why = "";
   s.use_global = false;
-  s.cfg_ok = !s.force_global && s.E < 65536 && bp_configure(s.dc, s.dv, s.m, d->n, d->num_sms, cfg, &why);
+  s.cfg_ok = !s.force_global && s.E < 65536 && bp_configure(s.dc, s.dv, s.m, d->n, s.hexp ? s.P : 0, d->num_sms, cfg, &why);
   if (!s.cfg_ok) {
     // no tile kernel for this side: the HBM-resident path takes over (still on the GPU; slower, see bp_global.cu)
     if (s.m > 65535) {

@@ -51,12 +51,15 @@ static BpKernel lookup_kernel(int dc, int dv, int vec, int guard, int m, int thr
   return nullptr;
 }
 
-bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, const char** why) {
+bool bp_configure(int dc, int dv, int m_code, int n, int qc_P, int num_sms, BpLaunch& cfg, const char** why) {
   static const char* kNoShape = "no compiled BP kernel for this (check degree, variable degree)";
   static const char* kNoFit = "one frame of messages does not fit in shared memory (such codes use the HBM-resident path)";
   static const char* kBadCfg = "invalid launch configuration";
-  if (!lookup_kernel(dc, dv, 1, 0, m)) { *why = kNoShape; return false; }
-  const int E = m * dc, mw = (m + 31) / 32, nw = (n + 31) / 32;
+  // the specialised instantiations lay their variable phase out by circulant column blocks (bp_kernel.cuh:var_phase)
+  const int spec_m = qc_P > 0 && qc_P * dv == m_code && n % qc_P == 0 ? m_code : 0;
+  cfg.spec_m = spec_m;
+  if (!lookup_kernel(dc, dv, 1, 0, spec_m)) { *why = kNoShape; return false; }
+  const int m = m_code, E = m * dc, mw = (m + 31) / 32, nw = (n + 31) / 32;
   if (E >= 65536) { *why = kNoFit; return false; }
   int dev = 0, smem_optin = 0, smem_sm = 0;
   cudaGetDevice(&dev);
@@ -71,7 +74,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
     for (int guard : {0, 1, 3, 4, 5, 7})
       for (int thr : {0, 128}) {  // generic instantiation and, where there is one, the one specialised for this code
         cudaFuncAttributes fa;
-        if (cudaFuncGetAttributes(&fa, lookup_kernel(dc, dv, v, guard, m, thr)) == cudaSuccess) r = std::max(r, fa.numRegs);
+        if (cudaFuncGetAttributes(&fa, lookup_kernel(dc, dv, v, guard, spec_m, thr)) == cudaSuccess) r = std::max(r, fa.numRegs);
       }
     cudaGetLastError();
     return std::max(r, 32);
@@ -119,7 +122,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
   // instantiation with different tile sizes), so it is raised to the device limit rather than to this tile's size.
   for (int guard : {0, 1, 3, 4, 5, 7})
     for (int thr : {0, 128}) {
-      if (cudaFuncSetAttribute(lookup_kernel(dc, dv, vec, guard, m, thr), cudaFuncAttributeMaxDynamicSharedMemorySize,
+      if (cudaFuncSetAttribute(lookup_kernel(dc, dv, vec, guard, spec_m, thr), cudaFuncAttributeMaxDynamicSharedMemorySize,
                                smem_optin) != cudaSuccess) {
         cudaGetLastError();
         *why = kNoFit;
@@ -127,7 +130,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
       }
     }
   const int regs = regs_of(vec);
-  BpKernel k = lookup_kernel(dc, dv, vec, 3, m, threads);
+  BpKernel k = lookup_kernel(dc, dv, vec, 3, spec_m, threads);
   if (threads % 32 || threads < 32 || threads > kMaxT) { *why = kBadCfg; return false; }
   int occ = 0;
   if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&occ, k, threads, smem) != cudaSuccess || occ < 1) {
@@ -148,7 +151,7 @@ bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, cons
 
 cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, int guard, cudaStream_t st) {
   if (args.trace_q || args.trace_r) guard += 4;  // the same instantiation with the message taps compiled in
-  BpKernel k = lookup_kernel(dc, dv, cfg.vec, guard, args.m, cfg.threads);
+  BpKernel k = lookup_kernel(dc, dv, cfg.vec, guard, cfg.spec_m, cfg.threads);
   if (!k) return cudaErrorInvalidDeviceFunction;
   const int tiles = (nframes + cfg.vec - 1) / cfg.vec;
   const int grid = std::max(1, std::min(cfg.grid, tiles));

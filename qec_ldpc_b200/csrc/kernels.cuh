@@ -15,11 +15,14 @@ struct BpLaunch {
   int smem = 0;      // dynamic shared memory per CTA
   int regs = 0;
   int max_threads = 0;
+  int spec_m = 0;    // check count the kernel is specialised for (0: generic instantiation), set by bp_configure
 };
 
 // Picks a kernel instantiation for (dc, dv), sizes the tile and fills `cfg` (zero fields = heuristic).
 // Returns false if no compiled instantiation covers the shape or the tile does not fit in shared memory.
-bool bp_configure(int dc, int dv, int m, int n, int num_sms, BpLaunch& cfg, const char** why);
+// qc_P: circulant size of a quasi-cyclic side (dv block rows, n / qc_P column blocks), 0 for any other code; the
+// instantiations specialised for a check count assume that structure.
+bool bp_configure(int dc, int dv, int m, int n, int qc_P, int num_sms, BpLaunch& cfg, const char** why);
 // guard: division range tests compiled in (0 none, 1 numerator, 3 both), see bp_kernel.cuh:div_fast
 cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, int nframes, int guard, cudaStream_t st);
 
