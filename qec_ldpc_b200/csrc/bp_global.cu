@@ -548,63 +548,82 @@ void pick_var(int dv, VarFn& fn, VarFn& fn_last, int& w) {
 #undef QLDPC_B
 }
 
-cudaError_t run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8_t* flags, uint32_t* iters, int nframes,
-                cudaStream_t st) {
-  const int m = a.m, n = a.n, E = a.m * a.dc;
-  // Slots in flight: enough that one pass moves ~1 GB (launch overhead out of sight), about a quarter of the frames
-  // so that every slot is refilled a few times and the straggler tail stays short, at most what was allocated.
-  const long long want = std::max<long long>(((long long)nframes + 3) / 4, (long long)(1.0e9 / (16.0 * E)));
-  const long long asked = a.slots > 0 ? ((long long)a.slots + 31) / 32 * 32 : (want + 127) / 128 * 128;
-  const int S = (int)std::max<long long>(32, std::min<long long>(a.batch, asked));
+// One run of one side, driven pass by pass so that the two sides of a decoder can be interleaved on two streams.
+struct GlobalRun {
+  static constexpr int kAhead = 8;  // passes enqueued beyond the one the host has seen finish
+  GlobalBpArgs a;
+  const uint32_t* syn = nullptr;
+  uint32_t* dec = nullptr;
+  uint8_t* flags = nullptr;
+  uint32_t* iters = nullptr;
+  int nframes = 0, S = 0, sb = 0, last_it = 0, wv = 1;
+  cudaStream_t st = nullptr;
   Slots s;
-  const int SW = S / 32;
-  s.msg = a.msg;
-  s.state = a.bytes;
-  s.bad = s.state + S;
-  s.nanflag = s.bad + S;
-  s.synw = a.words;
-  s.decw = s.synw + (size_t)m * SW;
-  s.mismatchw = s.decw + (size_t)n * SW;
-  s.donew = s.mismatchw + SW;
-  s.frame = (int32_t*)(a.words + ((size_t)(m + n + 2) * SW + 3) / 4 * 4);  // 16-byte aligned for the 4-slot loads
-  s.iter = s.frame + S;
-  s.ctr = (unsigned int*)(s.iter + S);
-  s.lastq = s.ctr + 4;
-  s.host_done = a.host_done;
   CheckFn check = nullptr;
   VarFn var = nullptr, var_last = nullptr;
-  int wc = 1, wv = 1;
-  pick_check(a.dc, check, wc);
-  pick_var(a.dv, var, var_last, wv);
-  const int sb = (S + kGroup - 1) / kGroup;
-  const dim3 gc((S + 128 * wc - 1) / (128 * wc), m), gv((S + 128 * wv - 1) / (128 * wv), n);
-  // the bit-word kernels: SW / 128 blocks of words, times enough y-strides over their units to fill the machine
-  const int vx = (SW + 127) / 128;
-  const dim3 ge(vx, std::max(1, std::min(m + a.nw, 4096 / std::max(vx, 1))));
-  const dim3 gf(vx, std::max(1, std::min(a.mw, 4096 / std::max(vx, 1))));
-  const int last_it = a.maxit - 1;
-  g_start<<<sb, kGroup, 0, st>>>(s, S);
+  dim3 gc, gv, ge, gf;
+  cudaEvent_t ev[kAhead] = {};
+  bool finished = false, begun = false;
+
+  cudaError_t begin(const GlobalBpArgs& a_, const uint32_t* syn_, uint32_t* dec_, uint8_t* flags_, uint32_t* iters_,
+                    int nframes_, cudaStream_t st_) {
+    a = a_; syn = syn_; dec = dec_; flags = flags_; iters = iters_; nframes = nframes_; st = st_;
+    begun = true;
+    const int m = a.m, n = a.n, E = a.m * a.dc;
+    // Slots in flight: enough that one pass moves ~1 GB (launch overhead out of sight), about a quarter of the frames
+    // so that every slot is refilled a few times and the straggler tail stays short, at most what was allocated.
+    const long long want = std::max<long long>(((long long)nframes + 3) / 4, (long long)(1.0e9 / (16.0 * E)));
+    const long long asked = a.slots > 0 ? ((long long)a.slots + 31) / 32 * 32 : (want + 127) / 128 * 128;
+    S = (int)std::max<long long>(32, std::min<long long>(a.batch, asked));
+    const int SW = S / 32;
+    s.msg = a.msg;
+    s.state = a.bytes;
+    s.bad = s.state + S;
+    s.nanflag = s.bad + S;
+    s.synw = a.words;
+    s.decw = s.synw + (size_t)m * SW;
+    s.mismatchw = s.decw + (size_t)n * SW;
+    s.donew = s.mismatchw + SW;
+    s.frame = (int32_t*)(a.words + ((size_t)(m + n + 2) * SW + 3) / 4 * 4);  // 16-byte aligned for the 4-slot loads
+    s.iter = s.frame + S;
+    s.ctr = (unsigned int*)(s.iter + S);
+    s.lastq = s.ctr + 4;
+    s.host_done = a.host_done;
+    int wc = 1;
+    pick_check(a.dc, check, wc);
+    pick_var(a.dv, var, var_last, wv);
+    sb = (S + kGroup - 1) / kGroup;
+    gc = dim3((S + 128 * wc - 1) / (128 * wc), m);
+    gv = dim3((S + 128 * wv - 1) / (128 * wv), n);
+    // the bit-word kernels: SW / 128 blocks of words, times enough y-strides over their units to fill the machine
+    const int vx = (SW + 127) / 128;
+    ge = dim3(vx, std::max(1, std::min(m + a.nw, 4096 / std::max(vx, 1))));
+    gf = dim3(vx, std::max(1, std::min(a.mw, 4096 / std::max(vx, 1))));
+    last_it = a.maxit - 1;
+    for (int i = 0; i < kAhead; ++i) {
+      cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
+      if (e != cudaSuccess) return e;
+    }
+    g_start<<<sb, kGroup, 0, st>>>(s, S);
+    return cudaGetLastError();
+  }
+
   // A pass first serves the slots that stopped in the previous pass (before the first pass: all of them, with no
   // frame to write out), then runs one BP iteration on every running slot.  Completion is read from mapped pinned
   // memory (g_control mirrors the count there); the host enqueues at most kAhead passes beyond the one it has seen
   // finish, so the device never waits for the host and the host never synchronises the stream inside a run.
   // Passes enqueued after the last frame has left find every slot idle and return at once.
-  constexpr int kAhead = 8;
-  cudaEvent_t ev[kAhead];
-  for (int i = 0; i < kAhead; ++i) {
-    cudaError_t e = cudaEventCreateWithFlags(&ev[i], cudaEventDisableTiming);
-    if (e != cudaSuccess) {
-      for (int j = 0; j < i; ++j) cudaEventDestroy(ev[j]);
-      return e;
-    }
-  }
-  cudaError_t err = cudaSuccess;
-  volatile unsigned int* host_done = a.host_done;
-  for (long long pass = 0;; ++pass) {
+  // Returns with `finished` set once the host has seen every frame leave.
+  cudaError_t step(long long pass) {
+    if (finished) return cudaSuccess;
+    const int n = a.n, m = a.m;
     if (pass >= kAhead) {
-      err = cudaEventSynchronize(ev[pass % kAhead]);  // pass - kAhead has finished
-      if (err != cudaSuccess) break;
-      if (*host_done >= (unsigned)nframes) break;
+      cudaError_t err = cudaEventSynchronize(ev[pass % kAhead]);  // pass - kAhead has finished
+      if (err != cudaSuccess) return err;
+      if (*(volatile unsigned int*)a.host_done >= (unsigned)nframes) {
+        finished = true;
+        return cudaSuccess;
+      }
     }
     if (pass > 0) g_verify_pack<<<ge, 128, 0, st>>>(s, a.cvar, m, a.dc, n, a.nw, S, dec);
     g_handover<<<sb, kGroup, 0, st>>>(s, S, nframes, flags, iters);
@@ -619,15 +638,20 @@ cudaError_t run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8
                                                                        s.lastq + (size_t)(parity ^ 1) * S,
                                                                        s.ctr + 2 + (parity ^ 1));
     g_control<<<sb, kGroup, 0, st>>>(s, S, last_it, wv, parity);
-    err = cudaEventRecord(ev[pass % kAhead], st);
-    if (err != cudaSuccess) break;
-    if (pass == 0 && (err = cudaGetLastError()) != cudaSuccess) break;  // a bad launch configuration shows here
+    cudaError_t err = cudaEventRecord(ev[pass % kAhead], st);
+    if (err != cudaSuccess) return err;
+    if (pass == 0) return cudaGetLastError();  // a bad launch configuration shows here
+    return cudaSuccess;
   }
-  if (err == cudaSuccess) err = cudaStreamSynchronize(st);  // drains the (empty) passes enqueued ahead
-  for (int i = 0; i < kAhead; ++i) cudaEventDestroy(ev[i]);
-  if (err != cudaSuccess) return err;
-  return cudaGetLastError();
-}
+
+  cudaError_t end(cudaError_t err) {
+    if (err == cudaSuccess && begun) err = cudaStreamSynchronize(st);  // drains the (empty) passes enqueued ahead
+    for (int i = 0; i < kAhead; ++i)
+      if (ev[i]) cudaEventDestroy(ev[i]);
+    if (err != cudaSuccess) return err;
+    return cudaGetLastError();
+  }
+};
 
 }  // namespace
 
@@ -645,7 +669,28 @@ cudaError_t global_bp_run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* 
   if (maxd > 32) return cudaErrorInvalidValue;
   if (nframes <= 0) return cudaSuccess;
   if (launches) *launches += 1;
-  return run(a, syn, dec, flags, iters, nframes, st);
+  GlobalRun r;
+  cudaError_t err = r.begin(a, syn, dec, flags, iters, nframes, st);
+  for (long long pass = 0; err == cudaSuccess && !r.finished; ++pass) err = r.step(pass);
+  return r.end(err);
+}
+
+// Both sides of a decoder at once, each on its own stream, their passes enqueued alternately by the one host thread:
+// the service kernels, launch gaps and straggler tail of one side are covered by the other side's message traffic.
+cudaError_t global_bp_run_pair(const GlobalBpArgs& ax, const uint32_t* synX, uint32_t* decX, uint8_t* flagsX, uint32_t* itersX,
+                               cudaStream_t stX, const GlobalBpArgs& az, const uint32_t* synZ, uint32_t* decZ,
+                               uint8_t* flagsZ, uint32_t* itersZ, cudaStream_t stZ, int nframes) {
+  if (std::max(std::max(ax.dc, ax.dv), std::max(az.dc, az.dv)) > 32) return cudaErrorInvalidValue;
+  if (nframes <= 0) return cudaSuccess;
+  GlobalRun r[2];
+  cudaError_t err = r[0].begin(ax, synX, decX, flagsX, itersX, nframes, stX);
+  if (err == cudaSuccess) err = r[1].begin(az, synZ, decZ, flagsZ, itersZ, nframes, stZ);
+  for (long long pass = 0; err == cudaSuccess && !(r[0].finished && r[1].finished); ++pass) {
+    err = r[0].step(pass);
+    if (err == cudaSuccess) err = r[1].step(pass);
+  }
+  const cudaError_t e0 = r[0].end(err), e1 = r[1].end(err);
+  return e0 != cudaSuccess ? e0 : e1;
 }
 
 }  // namespace qldpc

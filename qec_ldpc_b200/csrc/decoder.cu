@@ -409,6 +409,30 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
     CU_TRY(cudaEventRecord(d->ev_fork, d->stream));
     CU_TRY(cudaStreamWaitEvent(d->side_stream, d->ev_fork, 0));
   }
+  auto global_args = [&](const DevSide& s) {
+    GlobalBpArgs g;
+    g.m = s.m; g.n = d->n; g.dc = s.dc; g.dv = s.dv; g.mw = s.mw; g.nw = d->nw;
+    g.maxit = maxIterations; g.batch = s.gbatch; g.prior = prior;
+    g.slots = s.force_global ? s.user.threads : 0;
+    g.vrow = s.gvrow; g.cvar = s.gcvar; g.msg = s.gmsg; g.bytes = s.gbytes; g.words = s.gwords;
+    g.host_done = s.ghost_done;
+    return g;
+  };
+  // HBM-resident path on both sides: the two runs are interleaved on two streams (bp_global.cu:global_bp_run_pair); one
+  // timing bracket covers both, booked on the X side (the Z side counts its launch and no time of its own).
+  static const bool pair_runs = getenv("QLDPC_GLOBAL_SERIAL") == nullptr;
+  if (pair_runs && only_side < 0 && !trace_q && !trace_r && d->s[0].use_global && d->s[1].use_global && d->s[0].cfg_ok &&
+      d->s[1].cfg_ok && ensure_side_stream(d) == QLDPC_OK) {
+    d->launches[QLDPC_T_BP_Z] += 1;
+    Timed t(d, QLDPC_T_BP_X, 1, d->stream);
+    CU_TRY(cudaEventRecord(d->ev_fork, d->stream));
+    CU_TRY(cudaStreamWaitEvent(d->side_stream, d->ev_fork, 0));
+    CU_TRY(global_bp_run_pair(global_args(d->s[0]), synX, decX, sfX, itX, d->stream, global_args(d->s[1]), synZ, decZ, sfZ,
+                              itZ, d->side_stream, nf));
+    CU_TRY(cudaEventRecord(d->ev_join, d->side_stream));
+    CU_TRY(cudaStreamWaitEvent(d->stream, d->ev_join, 0));
+    return QLDPC_OK;
+  }
   for (int side = 0; side < 2; ++side) {
     if (only_side >= 0 && side != only_side) continue;
     DevSide& s = d->s[side];
@@ -430,13 +454,7 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
     Timed t(d, side ? QLDPC_T_BP_Z : QLDPC_T_BP_X, 1, st);
     if (s.use_global) {
       if (trace_q || trace_r) return fail(QLDPC_ERR_UNSUPPORTED, "message taps are not available on the global-memory path");
-      GlobalBpArgs g;
-      g.m = s.m; g.n = d->n; g.dc = s.dc; g.dv = s.dv; g.mw = s.mw; g.nw = d->nw;
-      g.maxit = maxIterations; g.batch = s.gbatch; g.prior = prior;
-      g.slots = s.force_global ? s.user.threads : 0;
-      g.vrow = s.gvrow; g.cvar = s.gcvar; g.msg = s.gmsg; g.bytes = s.gbytes; g.words = s.gwords;
-      g.host_done = s.ghost_done;
-      CU_TRY(global_bp_run(g, a.syn, a.dec, a.flags, a.iters, nf, nullptr, d->stream));
+      CU_TRY(global_bp_run(global_args(s), a.syn, a.dec, a.flags, a.iters, nf, nullptr, d->stream));
       continue;
     }
     CU_TRY(bp_launch(s.dc, s.dv, s.cfg, a, nf, division_guard(prior, s.dv), st));

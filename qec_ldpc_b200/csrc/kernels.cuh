@@ -41,6 +41,10 @@ struct GlobalBpArgs {
 size_t global_bp_bytes(int m, int n, int dc, int batch, size_t* msg_bytes, size_t* byte_bytes, size_t* word_bytes);
 cudaError_t global_bp_run(const GlobalBpArgs& a, const uint32_t* syn, uint32_t* dec, uint8_t* flags, uint32_t* iters,
                           int nframes, int* launches, cudaStream_t st);
+// X and Z side of one decoder concurrently on two streams (same results as two global_bp_run calls).
+cudaError_t global_bp_run_pair(const GlobalBpArgs& ax, const uint32_t* synX, uint32_t* decX, uint8_t* flagsX, uint32_t* itersX,
+                               cudaStream_t stX, const GlobalBpArgs& az, const uint32_t* synZ, uint32_t* decZ,
+                               uint8_t* flagsZ, uint32_t* itersZ, cudaStream_t stZ, int nframes);
 
 // Philox depolarizing errors, bit-packed: errX, errZ [nframes][nw], and their syndromes synX [nframes][mwX],
 // synZ [nframes][mwZ] in the same kernel (synX == nullptr: errors only).
