@@ -364,8 +364,14 @@ __device__ __forceinline__ void g_var_body(const Slots& s, const uint32_t* __res
   }
 }
 
+// Resident blocks per SM asked of the compiler for the hot variants: the kernel is bound by the bytes it keeps in flight
+// (a thread moves only dv * 16 B, and spends most of its lifetime waiting or computing with no load outstanding), so
+// occupancy is worth more than instructions or a few spilled registers here.  Measured on J4K5L10P61 (both sides
+// interleaved): 6 / 7 / 8 / 9 / 10 blocks of 128 threads -> 0.74 / 0.786 / 0.80 / 0.78 / 0.77 of the HBM roofline
+// (8 blocks = 64 registers, 8-32 B of spills).
+constexpr int var_min_blocks(int maxv, int w, bool last) { return !last && w == 4 && maxv <= 5 ? 8 : 1; }
 template <int MAXV, int W, bool EXACT, bool LAST>
-__global__ void __launch_bounds__(128) g_var(Slots s, const uint32_t* __restrict__ vrow, int n, int dv_rt, int S,
+__global__ void __launch_bounds__(128, var_min_blocks(MAXV, W, LAST)) g_var(Slots s, const uint32_t* __restrict__ vrow, int n, int dv_rt, int S,
                                              float prior, int last_it, const uint32_t* __restrict__ lastq,
                                              const unsigned int* __restrict__ lastq_len) {
   const int t = blockIdx.x * blockDim.x + threadIdx.x;
@@ -573,7 +579,9 @@ struct GlobalRun {
     // Slots in flight: enough that one pass moves ~1 GB (launch overhead out of sight), about a quarter of the frames
     // so that every slot is refilled a few times and the straggler tail stays short, at most what was allocated.
     const long long want = std::max<long long>(((long long)nframes + 3) / 4, (long long)(1.0e9 / (16.0 * E)));
-    const long long asked = a.slots > 0 ? ((long long)a.slots + 31) / 32 * 32 : (want + 127) / 128 * 128;
+    // (heuristic: at most 48k slots -- measured optimum of the n=610 code at 1M frames; beyond it the tail grows faster
+    // than the per-pass overheads shrink)
+    const long long asked = a.slots > 0 ? ((long long)a.slots + 31) / 32 * 32 : (std::min<long long>(want, 49152) + 127) / 128 * 128;
     S = (int)std::max<long long>(32, std::min<long long>(a.batch, asked));
     const int SW = S / 32;
     s.msg = a.msg;

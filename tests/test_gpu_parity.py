@@ -196,7 +196,7 @@ def test_zero_noise_and_saturated_noise(oracle, decoders):
 
 @pytest.mark.parametrize("code", ["C1", "C2"])
 @pytest.mark.parametrize("p", [1.5, 1.2, 0.0])
-def test_nan_messages_decide_like_the_reference(oracle, decoders, code, p):
+def test_nan_messages_decide_like_the_reference(qldpc, oracle, decoders, code, p):
     """prior = 2/3 p >= 1 (or 0) drives messages to 0/0: a NaN message compares false in the hard decision
     (DecoderCPU.h:354-373) and counts as converged (:231-246).  Decisions, flags and iteration counts per frame."""
     gc, dec = decoders(code)
@@ -212,6 +212,15 @@ def test_nan_messages_decide_like_the_reference(oracle, decoders, code, p):
     assert np.array_equal(ox, want["outX"]) and np.array_equal(oz, want["outZ"])
     assert np.array_equal(np.asarray(it).reshape(nf, 2), want["iters"])
     st = dec.get_stats_from_errors(x, z, p, 30, per_frame=True)
+    assert np.array_equal(st["flags"] & 63, want["flags"] & 63) and np.array_equal(st["counters"], want["counters"])
+    # the same through the HBM-resident kernel family
+    hbm = qldpc.Decoder(gc, 0, 4096)
+    for side in (0, 1):
+        hbm.configure(side, -1, 0, 0)
+    ox, oz, fl, it = hbm.decode_batch(sx, sz, p, 30)
+    assert np.array_equal(ox, want["outX"]) and np.array_equal(oz, want["outZ"])
+    assert np.array_equal(np.asarray(it).reshape(nf, 2), want["iters"])
+    st = hbm.get_stats_from_errors(x, z, p, 30, per_frame=True)
     assert np.array_equal(st["flags"] & 63, want["flags"] & 63) and np.array_equal(st["counters"], want["counters"])
 
 
