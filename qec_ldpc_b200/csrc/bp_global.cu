@@ -22,6 +22,7 @@
 // and read there; passes are enqueued at most 8 ahead of the device.
 #include <algorithm>
 #include <cstdint>
+#include <cstdlib>
 
 #include "kernels.cuh"
 
@@ -570,12 +571,14 @@ struct GlobalRun {
   VarFn var = nullptr, var_last = nullptr;
   dim3 gc, gv, ge, gf;
   cudaEvent_t ev[kAhead] = {};
-  bool finished = false, begun = false;
+  bool finished = false, begun = false, use_graphs = false;
+  cudaGraphExec_t gexec[4] = {};
 
   cudaError_t begin(const GlobalBpArgs& a_, const uint32_t* syn_, uint32_t* dec_, uint8_t* flags_, uint32_t* iters_,
                     int nframes_, cudaStream_t st_) {
     a = a_; syn = syn_; dec = dec_; flags = flags_; iters = iters_; nframes = nframes_; st = st_;
     begun = true;
+    use_graphs = nframes >= 4096 && getenv("QLDPC_GLOBAL_NO_GRAPH") == nullptr;  // short runs: not worth four captures
     const int m = a.m, n = a.n, E = a.m * a.dc;
     // Slots in flight: enough that one pass moves ~1 GB (launch overhead out of sight), about a quarter of the frames
     // so that every slot is refilled a few times and the straggler tail stays short, at most what was allocated.
@@ -625,7 +628,6 @@ struct GlobalRun {
   // Returns with `finished` set once the host has seen every frame leave.
   cudaError_t step(long long pass) {
     if (finished) return cudaSuccess;
-    const int n = a.n, m = a.m;
     if (pass >= kAhead) {
       cudaError_t err = cudaEventSynchronize(ev[pass % kAhead]);  // pass - kAhead has finished
       if (err != cudaSuccess) return err;
@@ -634,6 +636,36 @@ struct GlobalRun {
         return cudaSuccess;
       }
     }
+    // From the second pass on a pass is one of four fixed launch sequences (with / without the list-driven `last`
+    // launch, list parity 0 / 1): each is captured once per run and replayed as a CUDA graph, which takes the launch
+    // gaps between its 6-7 kernels from ~5 us to ~1 us.
+    const int gi = (pass >= last_it ? 2 : 0) + (int)(pass & 1);
+    if (use_graphs && pass > 0 && last_it > 0) {
+      cudaError_t err = cudaSuccess;
+      if (!gexec[gi]) {
+        cudaGraph_t g = nullptr;
+        err = cudaStreamBeginCapture(st, cudaStreamCaptureModeThreadLocal);
+        if (err == cudaSuccess) {
+          launch_pass(pass);
+          err = cudaStreamEndCapture(st, &g);
+        }
+        if (err == cudaSuccess) err = cudaGraphInstantiate(&gexec[gi], g, 0);
+        if (g) cudaGraphDestroy(g);
+        if (err != cudaSuccess) return err;
+      }
+      err = cudaGraphLaunch(gexec[gi], st);
+      if (err != cudaSuccess) return err;
+    } else {
+      launch_pass(pass);
+    }
+    cudaError_t err = cudaEventRecord(ev[pass % kAhead], st);
+    if (err != cudaSuccess) return err;
+    if (pass == 0) return cudaGetLastError();  // a bad launch configuration shows here
+    return cudaSuccess;
+  }
+
+  void launch_pass(long long pass) {
+    const int n = a.n, m = a.m;
     if (pass > 0) g_verify_pack<<<ge, 128, 0, st>>>(s, a.cvar, m, a.dc, n, a.nw, S, dec);
     g_handover<<<sb, kGroup, 0, st>>>(s, S, nframes, flags, iters);
     g_fill<<<gf, 128, 0, st>>>(s, syn, a.mw, m, S);
@@ -647,16 +679,14 @@ struct GlobalRun {
                                                                        s.lastq + (size_t)(parity ^ 1) * S,
                                                                        s.ctr + 2 + (parity ^ 1));
     g_control<<<sb, kGroup, 0, st>>>(s, S, last_it, wv, parity);
-    cudaError_t err = cudaEventRecord(ev[pass % kAhead], st);
-    if (err != cudaSuccess) return err;
-    if (pass == 0) return cudaGetLastError();  // a bad launch configuration shows here
-    return cudaSuccess;
   }
 
   cudaError_t end(cudaError_t err) {
     if (err == cudaSuccess && begun) err = cudaStreamSynchronize(st);  // drains the (empty) passes enqueued ahead
     for (int i = 0; i < kAhead; ++i)
       if (ev[i]) cudaEventDestroy(ev[i]);
+    for (int i = 0; i < 4; ++i)
+      if (gexec[i]) cudaGraphExecDestroy(gexec[i]);
     if (err != cudaSuccess) return err;
     return cudaGetLastError();
   }

@@ -338,6 +338,27 @@ def test_global_memory_path_matches_oracle(qldpc, oracle, code, nf):
     assert np.array_equal(dec.get_statistics_depolarizing(77, 3, nf, p, maxit)["counters"], b["counters"])
 
 
+def test_global_memory_path_large_batch_graph_replay(qldpc, oracle):
+    """Batches of 4096 frames and more replay each pass of the HBM-resident path as a CUDA graph, X and Z interleaved on
+    two streams; few slots (many refills per slot) and one iteration cap below and above the graph switch-over.
+    Counters, flags and iteration counts against the oracle, and against the serial, graph-free run of one side."""
+    gc = qldpc.Code.qc(*CODES["C2"])
+    oc = ocode(oracle, "C2", gc)
+    dec = qldpc.Decoder(gc, 0, 8192)
+    for maxit, slots in ((50, 1024), (12, 0), (1, 0)):
+        for side in (0, 1):
+            dec.configure(side, -1, slots, 0)
+        a = dec.get_statistics_depolarizing(5, 11, 6000, 0.06, maxit, per_frame=True)
+        b = oc.run_depolarizing(5, 11, 6000, 0.06, maxit)
+        assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
+        assert np.array_equal(a["iters"], b["iters"].astype(np.uint32))
+    # one side on the HBM-resident path, the other on the tile kernel (no pairing)
+    dec.configure(1, 0, 0, 0)
+    a = dec.get_statistics_depolarizing(5, 11, 6000, 0.06, 50, per_frame=True)
+    b = oc.run_depolarizing(5, 11, 6000, 0.06, 50)
+    assert np.array_equal(a["counters"], b["counters"]) and np.array_equal(a["flags"], b["flags"])
+
+
 @pytest.mark.parametrize("prm,shapes", [((3, 4, 8, 13, 5, 2), ((8, 3), (8, 4))), ((6, 6, 12, 7, 3, 2), ((12, 6), (12, 6))),
                                         ((3, 4, 10, 31, 2, 2), ((10, 3), (10, 4))), ((3, 4, 12, 13, 4, 2), ((12, 3), (12, 4))),
                                         ((5, 6, 12, 37, 11, 2), ((12, 5), (12, 6))), ((2, 3, 6, 7, 2, 3), ((6, 2), (6, 3))),
