@@ -167,7 +167,11 @@ __global__ void __launch_bounds__(128, (EXACT && W == 4 && MAXC <= 12) ? 7 : 1) 
 // full-product registers: higher occupancy for a bandwidth-bound kernel), LAST = true the others (DecoderCPU.h:284).
 // The latter works from the list g_control compiled in the previous pass (`lastq`, usually empty or short), or
 // over all threads if `lastq` is null (one-iteration runs, where every slot is in its last iteration).
-template <int MAXV, int W, bool EXACT, bool LAST>
+// GUARD: the division range tests of the hot variant, as in the tile kernel (decoder.cu:division_guard): 0 = the host
+// proved that neither can fire, 1 = only the numerator test could, and the product chains run scaled by 2^64 instead
+// (exact, bp_kernel.cuh:var_phase), 3 = both tests with the __fdiv_rn fallback.  The tests and the fallback's control flow
+// are a fifth of this kernel's instructions, and it runs at 60% issue utilisation next to its memory traffic.
+template <int MAXV, int W, bool EXACT, bool LAST, int GUARD = 3>
 __device__ __forceinline__ void g_var_body(const Slots& s, const uint32_t* __restrict__ vrow, int n, int dv_rt, int S,
                                            float prior, int last_it, int t, int v) {
   const int dv = EXACT ? MAXV : dv_rt;
@@ -243,6 +247,9 @@ __device__ __forceinline__ void g_var_body(const Slots& s, const uint32_t* __res
     constexpr int H = W / 2;
     typedef Pack<2> P2;
     P2 pk2[MAXV][H], om2[MAXV][H], pP[H], pQ[H];
+    uint32_t lowest[W];
+#pragma unroll
+    for (int w = 0; w < W; ++w) lowest[w] = 0xFFFFFFFFu;
 #pragma unroll
     for (int k = 0; k < MAXV; ++k)
       if (k < dv) {
@@ -252,8 +259,10 @@ __device__ __forceinline__ void g_var_body(const Slots& s, const uint32_t* __res
           om2[k][h] = pfma(pk2[k][h], P2::splat(-1.0f), P2::splat(1.0f));  // 1 - p, one rounding (DecoderCPU.h:220)
         }
       }
+    constexpr int kTests = GUARD == 1 ? 0 : GUARD;
+    const float scale = GUARD == 1 ? 18446744073709551616.0f : 1.0f;  // 2^64
 #pragma unroll
-    for (int h = 0; h < H; ++h) { pP[h] = P2::splat(prior); pQ[h] = P2::splat(prior1); }
+    for (int h = 0; h < H; ++h) { pP[h] = P2::splat(__fmul_rn(prior, scale)); pQ[h] = P2::splat(__fmul_rn(prior1, scale)); }
 #pragma unroll
     for (int j = 0; j < MAXV; ++j) {
       if (j < dv) {
@@ -271,8 +280,8 @@ __device__ __forceinline__ void g_var_body(const Slots& s, const uint32_t* __res
           nden.set(0, __fadd_rn(-Q.get(0), -P.get(0)));
           nden.set(1, __fadd_rn(-Q.get(1), -P.get(1)));
           bool unsafe = false;
-          P2 out = div_fast_pack<3, 2>(P, nden, unsafe);  // == P / (Q + P), DecoderCPU.h:223
-          if (unsafe) {
+          P2 out = div_fast_pack<kTests, 2>(P, nden, unsafe);  // == P / (Q + P), DecoderCPU.h:223
+          if (kTests != 0 && unsafe) {
             out.set(0, __fdiv_rn(P.get(0), -nden.get(0)));
             out.set(1, __fdiv_rn(P.get(1), -nden.get(1)));
           }
@@ -285,13 +294,18 @@ __device__ __forceinline__ void g_var_body(const Slots& s, const uint32_t* __res
         }
 #pragma unroll
         for (int w = 0; w < W; ++w) {
-          anybad[w] |= unconverged(q[w]);
+          // saturation test as a running minimum in a volatile asm statement (bp_kernel.cuh:sat_update): without the
+          // range tests' control flow around it, the plain comparison came out of CUDA 12.9 reporting converged slots
+          // as unconverged here as well (10 extra iterations; the parity tests of this path catch it)
+          sat_update(lowest[w], q[w]);
           anynan[w] |= q[w] != q[w];
           bit[w] |= q[w] >= 0.5f;  // hard decision: any edge message >= 0.5f (DecoderCPU.h:354-373)
         }
         st_f<W>(s.msg + (size_t)row[j] * S + f, q);
       }
     }
+#pragma unroll
+    for (int w = 0; w < W; ++w) anybad[w] = lowest[w] < (0x3F7D70A4u - 0x3C23D70Au - 1u);  // == OR of unconverged(q)
   } else {
 #pragma unroll
   for (int j = 0; j < MAXV; ++j) {
@@ -372,7 +386,7 @@ __device__ __forceinline__ void g_var_body(const Slots& s, const uint32_t* __res
 // interleaved): 6 / 7 / 8 / 9 / 10 blocks of 128 threads -> 0.74 / 0.786 / 0.80 / 0.78 / 0.77 of the HBM roofline
 // (8 blocks = 64 registers, 8-32 B of spills).
 constexpr int var_min_blocks(int maxv, int w, bool last) { return !last && w == 4 && maxv <= 5 ? 8 : 1; }
-template <int MAXV, int W, bool EXACT, bool LAST>
+template <int MAXV, int W, bool EXACT, bool LAST, int GUARD = 3>
 __global__ void __launch_bounds__(128, var_min_blocks(MAXV, W, LAST)) g_var(Slots s, const uint32_t* __restrict__ vrow, int n, int dv_rt, int S,
                                              float prior, int last_it, const uint32_t* __restrict__ lastq,
                                              const unsigned int* __restrict__ lastq_len) {
@@ -382,9 +396,9 @@ __global__ void __launch_bounds__(128, var_min_blocks(MAXV, W, LAST)) g_var(Slot
     // and a full-size grid of threads that only find that out costs as much as a tenth of a pass.
     const int len = (int)*lastq_len;
     for (int li = t; li < len; li += gridDim.x * blockDim.x)
-      g_var_body<MAXV, W, EXACT, LAST>(s, vrow, n, dv_rt, S, prior, last_it, (int)lastq[li], blockIdx.y);
+      g_var_body<MAXV, W, EXACT, LAST, GUARD>(s, vrow, n, dv_rt, S, prior, last_it, (int)lastq[li], blockIdx.y);
   } else {
-    g_var_body<MAXV, W, EXACT, LAST>(s, vrow, n, dv_rt, S, prior, last_it, t, blockIdx.y);
+    g_var_body<MAXV, W, EXACT, LAST, GUARD>(s, vrow, n, dv_rt, S, prior, last_it, t, blockIdx.y);
   }
 }
 
@@ -545,7 +559,17 @@ void pick_check(int dc, CheckFn& fn, int& w) {
 #undef QLDPC_E
 #undef QLDPC_B
 }
-void pick_var(int dv, VarFn& fn, VarFn& fn_last, int& w) {
+void pick_var(int dv, int guard, VarFn& fn, VarFn& fn_last, int& w) {
+  // the common small degrees also come without the division range tests / with scaled chains (g_var_body: GUARD)
+#define QLDPC_G(N)                                                                                        \
+  if (dv == N && guard != 3) {                                                                            \
+    fn = guard == 0 ? g_var<N, var_width(N), true, false, 0> : g_var<N, var_width(N), true, false, 1>;    \
+    fn_last = g_var<N, var_width(N), true, true>;                                                         \
+    w = var_width(N);                                                                                     \
+    return;                                                                                               \
+  }
+  QLDPC_G(2) QLDPC_G(3) QLDPC_G(4) QLDPC_G(5) QLDPC_G(6)
+#undef QLDPC_G
 #define QLDPC_E(N) \
   if (dv == N) { fn = g_var<N, var_width(N), true, false>; fn_last = g_var<N, var_width(N), true, true>; w = var_width(N); return; }
 #define QLDPC_B(N) \
@@ -603,7 +627,7 @@ struct GlobalRun {
     s.host_done = a.host_done;
     int wc = 1;
     pick_check(a.dc, check, wc);
-    pick_var(a.dv, var, var_last, wv);
+    pick_var(a.dv, a.guard, var, var_last, wv);
     sb = (S + kGroup - 1) / kGroup;
     gc = dim3((S + 128 * wc - 1) / (128 * wc), m);
     gv = dim3((S + 128 * wv - 1) / (128 * wv), n);

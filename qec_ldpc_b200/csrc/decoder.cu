@@ -416,6 +416,7 @@ int run_bp(qldpc_decoder* d, const uint32_t* synX, const uint32_t* synZ, int nf,
     g.slots = s.force_global ? s.user.threads : 0;
     g.vrow = s.gvrow; g.cvar = s.gcvar; g.msg = s.gmsg; g.bytes = s.gbytes; g.words = s.gwords;
     g.host_done = s.ghost_done;
+    g.guard = division_guard(prior, s.dv);
     return g;
   };
   // HBM-resident path on both sides: the two runs are interleaved on two streams (bp_global.cu:global_bp_run_pair); one

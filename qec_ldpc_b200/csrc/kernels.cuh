@@ -30,6 +30,7 @@ cudaError_t bp_launch(int dc, int dv, const BpLaunch& cfg, const BpArgs& args, i
 struct GlobalBpArgs {
   int m, n, dc, dv, mw, nw, maxit, batch;
   int slots = 0;         // frame slots in flight (0 = heuristic), at most `batch`
+  int guard = 3;         // division range tests outside the last iteration: 0 / 1 / 3 (decoder.cu:division_guard)
   float prior;
   const uint32_t* vrow;  // [dv][n]
   const uint32_t* cvar;  // [dc][m]
